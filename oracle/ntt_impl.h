@@ -1,0 +1,117 @@
+/*
+ * oracle/ntt_impl.h — TEST INFRASTRUCTURE (CPU oracle), not product code.
+ *
+ * Radix-2 NTT over a Pasta field, restating ark-poly 0.5.0 Radix2EvaluationDomain::{fft,ifft}_in_place
+ * (crate pinned in Cargo.lock:171-279, source not on disk) as reached from the reference at
+ * kimchi/src/prover.rs:289,377,907,1163, kimchi/src/circuits/constraints.rs:494,
+ * poly-commitment/src/utils.rs:195-198 (list: SURVEY.md §8 row a8):
+ *   forward  out[i] = sum_j a[j] * (g*w^i)^j      (g = 1 for a plain domain, g = 5 for the default coset)
+ *   inverse  a[j]   = g^{-j} * n^{-1} * sum_i out[i] * w^{-ij}
+ * natural order in and out, w = ROOT^(2^(32-log_n)), elements in Montgomery form.
+ * The w / index order / 1/n conventions are pinned by the Lagrange-basis golden vectors of
+ * srs/test_*.srs (produced by the same generic routine, poly-commitment/src/ipa.rs:1161).
+ *
+ * Shape follows the CPU cost model of the reference: per-call root table of n/2
+ * entries, log n butterfly layers parallelised per layer, one bit-reversal permutation.
+ */
+
+static void FN(bitrev_permute)(FN(t) *a, unsigned log_n) {
+    size_t n = (size_t)1 << log_n;
+    for (size_t i = 0; i < n; i++) {
+        size_t r = 0;
+        for (unsigned b = 0; b < log_n; b++) r |= ((i >> b) & 1) << (log_n - 1 - b);
+        if (i < r) { FN(t) t = a[i]; a[i] = a[r]; a[r] = t; }
+    }
+}
+
+/* in-place, natural in -> natural out, using root w (order n) */
+static void FN(ntt_core)(FN(t) *a, unsigned log_n, const FN(t) *w, int threads) {
+    size_t n = (size_t)1 << log_n;
+    if (n == 1) return;
+    /* roots[i] = w^i, i < n/2 */
+    FN(t) *roots = (FN(t) *)malloc((n / 2) * sizeof(FN(t)));
+    {
+        /* blocked so it can be parallelised like ark's roots_of_unity */
+        size_t half = n / 2;
+        size_t blk = 1024;
+        size_t nblk = (half + blk - 1) / blk;
+        FN(t) wblk; FN(pow_u64)(&wblk, w, blk);
+        FN(t) *starts = (FN(t) *)malloc(nblk * sizeof(FN(t)));
+        FN(set_one)(&starts[0]);
+        for (size_t b = 1; b < nblk; b++) FN(mul)(&starts[b], &starts[b - 1], &wblk);
+#pragma omp parallel for num_threads(threads) schedule(static)
+        for (size_t b = 0; b < nblk; b++) {
+            FN(t) cur = starts[b];
+            size_t end = (b + 1) * blk < half ? (b + 1) * blk : half;
+            for (size_t i = b * blk; i < end; i++) { roots[i] = cur; FN(mul)(&cur, &cur, w); }
+        }
+        free(starts);
+    }
+    /* decimation in frequency: natural in, bit-reversed out */
+    for (unsigned s = 0; s < log_n; s++) {
+        size_t half = n >> (s + 1);        /* butterfly span */
+        size_t step = (size_t)1 << s;      /* root stride */
+#pragma omp parallel for num_threads(threads) schedule(static) if (n >= 4096)
+        for (size_t k = 0; k < n / 2; k++) {
+            size_t grp = k / half, j = k % half;
+            size_t i0 = grp * 2 * half + j, i1 = i0 + half;
+            FN(t) u = a[i0], v = a[i1], d;
+            FN(add)(&a[i0], &u, &v);
+            FN(sub)(&d, &u, &v);
+            FN(mul)(&a[i1], &d, &roots[j * step]);
+        }
+    }
+    free(roots);
+    FN(bitrev_permute)(a, log_n);
+}
+
+static void FN(ntt)(FN(t) *a, unsigned log_n, int inverse, int coset, int threads) {
+    size_t n = (size_t)1 << log_n;
+    FN(t) w; FN(root_of_unity)(&w, log_n);
+    FN(t) g;
+    { uint64_t c5[4] = {5, 0, 0, 0}; FN(to_mont)(&g, c5); }
+    if (!inverse) {
+        if (coset) {
+            FN(t) p; FN(set_one)(&p);
+            for (size_t i = 0; i < n; i++) { FN(mul)(&a[i], &a[i], &p); FN(mul)(&p, &p, &g); }
+        }
+        FN(ntt_core)(a, log_n, &w, threads);
+    } else {
+        FN(t) wi; FN(inv)(&wi, &w);
+        FN(ntt_core)(a, log_n, &wi, threads);
+        FN(t) ninv, nn;
+        uint64_t nc[4] = {(uint64_t)n, 0, 0, 0};
+        FN(to_mont)(&nn, nc);
+        FN(inv)(&ninv, &nn);
+        FN(t) gi; FN(inv)(&gi, &g);
+        FN(t) p = ninv;
+        for (size_t i = 0; i < n; i++) {
+            FN(mul)(&a[i], &a[i], &p);
+            if (coset) FN(mul)(&p, &p, &gi);
+        }
+    }
+}
+
+/* definition-level O(n^2) transform for tiny cross-checks */
+static void FN(dft_naive)(FN(t) *out, const FN(t) *in, unsigned log_n, int inverse) {
+    size_t n = (size_t)1 << log_n;
+    FN(t) w; FN(root_of_unity)(&w, log_n);
+    if (inverse) FN(inv)(&w, &w);
+    for (size_t i = 0; i < n; i++) {
+        FN(t) wi; FN(pow_u64)(&wi, &w, i);
+        FN(t) acc; FN(set_zero)(&acc);
+        FN(t) p; FN(set_one)(&p);
+        for (size_t j = 0; j < n; j++) {
+            FN(t) t; FN(mul)(&t, &in[j], &p);
+            FN(add)(&acc, &acc, &t);
+            FN(mul)(&p, &p, &wi);
+        }
+        out[i] = acc;
+    }
+    if (inverse) {
+        FN(t) ninv, nn;
+        uint64_t nc[4] = {(uint64_t)n, 0, 0, 0};
+        FN(to_mont)(&nn, nc); FN(inv)(&ninv, &nn);
+        for (size_t i = 0; i < n; i++) FN(mul)(&out[i], &out[i], &ninv);
+    }
+}
