@@ -1,0 +1,342 @@
+#!/usr/bin/env python3
+"""bench.py — Pallas MSM points/s (+ Fp NTT elements/s) at 2^16 on B200, next to the CPU oracle on the same host.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA library through its C ABI)
+    python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port of the reference's ark MSM/FFT
+    torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1: one rank per GPU
+
+A "step" is one pass of the hot path over one batch of synthetic input: one 2^16-point Pallas MSM (BASELINE config 2)
+followed by one 2^16-element Fp NTT.  The headline metric is the MSM's points/s; the NTT is reported in `ntt`.
+  value  : inputs already resident in HBM, device time per step from CUDA events on the launching stream
+  e2e    : the same step through the host-pointer C-ABI calls (zk_msm / zk_ntt_batch): scalars and polynomial start in
+           PINNED host memory, H2D and D2H inside the timed region
+N > 1 (weak scaling): every rank holds the SRS and runs its own 2^16-point slice of an (N * 2^16)-point MSM; the N
+Jacobian partials (96 B each) are exchanged with one NCCL all_gather and summed.  NTT: N independent replicas.
+Between timed iterations a 256 MiB buffer is overwritten to flush the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 16
+N_PTS = 1 << LOG_N
+MSM_BYTES_PER_POINT = 96      # 64 B affine base + 32 B scalar
+NTT_BYTES_PER_ELEM = 64       # 32 B read + 32 B write per transform
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(orc, rank):
+    """Pallas SRS generators (the reference's own srs/pallas.srs, via tests/golden) + seeded scalars / polynomial."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pallas_srs.npz"))
+    g = orc.decompress(orc.PALLAS, z["g_cmp"].tobytes())           # input preparation only
+    scalars = orc.random_scalars(orc.FQ, N_PTS, seed=1 + rank)     # canonical (msm_bigint form)
+    poly = orc.to_mont(orc.FP, orc.random_scalars(orc.FP, N_PTS, seed=2))
+    return g, scalars, poly
+
+
+def cpu_time(fn, min_seconds, max_reps):
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        fn()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds or reps >= max_reps:
+            return el / reps, reps
+
+
+def run_reference(args):
+    """The reference's CPU path for this workload, as restated by the oracle (oracle/pasta_oracle.c: ark-style signed-digit
+    Pippenger with window-parallel threads; ark-style radix-2 FFT), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    threads = orc.lib().orc_max_threads()
+    g, scalars, poly = make_inputs(orc, 0)
+    for _ in range(max(1, args.warmup)):
+        orc.msm(orc.PALLAS, g, scalars)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.msm(orc.PALLAS, g, scalars)
+    msm_s = (time.perf_counter() - t0) / args.steps
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.ntt(orc.FP, poly)
+    ntt_s = (time.perf_counter() - t0) / args.steps
+    val = N_PTS / msm_s
+    sample = f"{args.steps} x (one 2^16-point Pallas MSM, uniform scalars) after {max(1, args.warmup)} warm-up"
+    line = {
+        "impl": "reference", "metric": "pallas_msm_points_per_s", "value": val, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": msm_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 (4 x u64 Montgomery limbs)", "data": "synthetic",
+        "config": {"workload": "2^16-point Pallas MSM on srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)",
+                   "cpu_path": "oracle port of ark-ec 0.5 msm_bigint (reference is Rust; no cargo in the image)"},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ntt": {"metric": "fp_ntt_elements_per_s", "value": N_PTS / ntt_s, "unit": "elements/s", "ms": ntt_s * 1e3,
+                "workload": "2^16-element Fp forward NTT", "cores": threads},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--window-bits", type=int, default=-1, help="table window of the resident SRS (-1: library default; 16 = BASELINE config 2's w)")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="budget of the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import proof_systems_b200 as zk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: proof_systems_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oracle import oracle as orc   # input preparation + the cpu_baseline leg + the correctness check of the timed result
+
+    g, scalars, poly = make_inputs(orc, rank)
+    ctx = zk.Context(local)
+    stream = torch.cuda.Stream(device=local)
+    ctx.set_stream(stream.cuda_stream)
+    bases = ctx.upload_bases(zk.PALLAS, g, window_bits=args.window_bits)
+    wb = bases.window_bits
+
+    # device-resident inputs (value) and pinned host inputs (e2e)
+    d_scalars = torch.from_numpy(scalars.view(np.int64)).cuda()
+    d_poly0 = torch.from_numpy(poly.view(np.int64)).cuda()
+    d_poly = d_poly0.clone()
+    h_scalars = torch.from_numpy(scalars.view(np.int64)).pin_memory()
+    h_poly = torch.from_numpy(poly.view(np.int64).copy()).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush.fill_(rank + 1)
+
+    from proof_systems_b200.parallel import all_gather_point_sum
+
+    def reduce_partials(jac):
+        """final point-sum: one NCCL all_gather of the 96-byte Jacobian partials, then N-1 additions"""
+        return all_gather_point_sum(zk.PALLAS, jac, device=torch.device("cuda", local))
+
+    def step_resident():
+        jac = ctx.msm_dev(bases, d_scalars.data_ptr(), N_PTS)
+        return reduce_partials(jac)
+
+    def ntt_resident():
+        ctx.ntt_dev(zk.FP, d_poly.data_ptr(), LOG_N)
+
+    def step_e2e():
+        jac = ctx_msm_host()
+        return reduce_partials(jac)
+
+    import ctypes
+
+    from proof_systems_b200._lib import _u64p, check
+
+    def ctx_msm_host():
+        out = np.empty(12, dtype=np.uint64)
+        check(zk.lib().zk_msm(ctx._h, bases._h, 0, N_PTS, ctypes.c_void_p(h_scalars.data_ptr()), 0, 0, out.ctypes.data_as(_u64p)))
+        return out
+
+    def ntt_e2e():
+        check(zk.lib().zk_ntt_batch(ctx._h, zk.FP, ctypes.c_void_p(h_poly.data_ptr()), LOG_N, 1, 0, 0, 0))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """per-step CUDA events on the launching stream, L2 flushed between steps (outside the timed span)"""
+        tot = 0.0
+        for _ in range(steps):
+            flush_l2()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (also checks the result that is about to be timed against the CPU oracle, rank 0)
+    result = None
+    for _ in range(args.warmup):
+        result = step_resident()
+        ntt_resident()
+        step_e2e()
+        ntt_e2e()
+    barrier()
+    launches0 = ctx.launch_count
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    msm_ms = timed(step_resident, args.steps)
+    barrier()
+    launches_msm = ctx.launch_count - launches0
+    ntt_ms = timed(ntt_resident, args.steps)
+    barrier()
+    msm_e2e_ms = timed(step_e2e, args.steps)
+    barrier()
+    ntt_e2e_ms = timed(ntt_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches_total = ctx.launch_count - launches0
+
+    # ---- dominant-kernel durations, live, with CUDA events inside the library (profiling mode, separate pass)
+    ctx.set_profile(True)
+    acc_ms, ntt_kern_ms, stages = [], [], None
+    for _ in range(min(args.steps, 10)):
+        flush_l2()
+        torch.cuda.synchronize()
+        ctx.msm_dev(bases, d_scalars.data_ptr(), N_PTS)
+        stages = ctx.last_stage_ms()
+        acc_ms.append(stages["accumulate"])
+        ctx.ntt_dev(zk.FP, d_poly.data_ptr(), LOG_N)
+        ntt_kern_ms.append(ctx.last_stage_ms()["ntt"])
+    ctx.set_profile(False)
+
+    msm_ms, ntt_ms = max_over_ranks(msm_ms), max_over_ranks(ntt_ms)
+    msm_e2e_ms, ntt_e2e_ms = max_over_ranks(msm_e2e_ms), max_over_ranks(ntt_e2e_ms)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- correctness of what was timed + CPU baseline on the same host (bounded sample)
+    threads = orc.lib().orc_max_threads()
+    if world == 1:
+        want = orc.msm(orc.PALLAS, g, scalars)
+    else:
+        tot = [0] * N_PTS
+        m = orc.FQ_MODULUS
+        for r in range(world):
+            sr = orc.limbs_to_ints(orc.random_scalars(orc.FQ, N_PTS, seed=1 + r))
+            tot = [(a + b) % m for a, b in zip(tot, sr)]
+        want = orc.msm(orc.PALLAS, g, orc.ints_to_limbs(tot))
+    ok = bool(np.array_equal(zk.jacobian_to_affine(zk.PALLAS, result), want))
+    cpu_msm_s, cpu_reps = cpu_time(lambda: orc.msm(orc.PALLAS, g, scalars), args.cpu_seconds, 50)
+    cpu_ntt_s, cpu_ntt_reps = cpu_time(lambda: orc.ntt(orc.FP, poly), args.cpu_seconds / 3, 200)
+
+    peak, peak_src = load_peaks()
+    per_step_ms = msm_ms / args.steps
+    value = world * N_PTS / (per_step_ms * 1e-3)
+    e2e_value = world * N_PTS / (msm_e2e_ms / args.steps * 1e-3)
+    acc = float(np.median(acc_ms))
+    achieved = MSM_BYTES_PER_POINT * N_PTS / (acc * 1e-3) / 1e9
+    ntt_k = float(np.median(ntt_kern_ms))
+    ntt_ach = NTT_BYTES_PER_ELEM * N_PTS / (ntt_k * 1e-3) / 1e9
+    line = {
+        "metric": "pallas_msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (8 x u32 Montgomery limbs)", "data": "synthetic",
+        "config": {
+            "workload": "2^16-point Pallas MSM on the reference's srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)"
+                        + ("" if world == 1 else f"; rank r adds its own 2^16-scalar slice: one {world * N_PTS}-point MSM, all_gather of 96 B partials"),
+            "window_bits": wb, "resident_table_mib": round(len(bases) * 64 * ((256 + wb - 1) // wb if wb else 1) / 2**20, 1),
+            "l2": "256 MiB buffer overwritten between timed iterations (flush)", "result_matches_cpu_oracle": ok,
+        },
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": N_PTS * 32, "d2h_bytes_per_step": 96 + 128 * max(wb, 1),
+                "ms_per_step": msm_e2e_ms / args.steps},
+        "gpu_launches": int(launches_total),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_accumulate (bucket accumulation)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acc,
+                     "note": "MSM is integer-ALU bound: 96 B/point of compulsory traffic vs ~16 mixed additions (160 modmul) per point",
+                     "stage_ms": stages},
+        "cpu_baseline": {"value": N_PTS / cpu_msm_s, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": f"{cpu_reps} x the same 2^16-point MSM (oracle: ark-style Pippenger, {threads} threads), {cpu_msm_s * 1e3:.1f} ms each"},
+        "ntt": {
+            "metric": "fp_ntt_elements_per_s", "workload": "2^16-element Fp forward NTT (Radix2EvaluationDomain::fft_in_place)" + ("" if world == 1 else f", {world} replicas"),
+            "value": world * N_PTS / (ntt_ms / args.steps * 1e-3), "unit": "elements/s", "ms_per_step": ntt_ms / args.steps,
+            "e2e": {"value": world * N_PTS / (ntt_e2e_ms / args.steps * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": N_PTS * 32, "d2h_bytes_per_step": N_PTS * 32},
+            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass x2", "achieved": ntt_ach, "peak": peak, "unit": "GB/s", "frac": ntt_ach / peak, "traffic": None, "kernel_ms": ntt_k},
+            "cpu_baseline": {"value": N_PTS / cpu_ntt_s, "unit": "elements/s", "cores": threads, "kind": "port", "sample": f"{cpu_ntt_reps} x the same transform"},
+        },
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+/*
+ * zkb200.h — C ABI of the B200-native MSM + NTT hot path of o1-labs/proof-systems (Kimchi).
+ *
+ * The reference has NO C ABI or plugin loader on this path: its seam is two Rust traits and one arkworks trait
+ * (SURVEY.md §8b).  These entry points are what a Rust `extern "C"` block behind those traits binds
+ * (INTEGRATION.md shows the shim); each one names the reference interface it replaces.
+ *
+ * Conventions (identical to the reference's in-memory representation, so no re-encoding at the boundary):
+ *   field element   4 x uint64_t little-endian limbs, MONTGOMERY form (R = 2^256) unless a parameter says canonical
+ *                   == ark_ff::Fp256<MontBackend<_,4>>.0.0   (curves/src/pasta/fields/fp.rs:8-12, fq.rs:8-12;
+ *                   the reference itself treats Fp as raw limbs in kimchi/src/cached_prover_index.rs:486-530)
+ *   affine point    x || y, 8 x uint64_t; the identity (Affine{infinity: true},
+ *                   poly-commitment/src/commitment.rs:563-569) is encoded as all zeros — (0,0) is not on y^2 = x^3 + 5
+ *   Jacobian point  X || Y || Z, 12 x uint64_t, x = X/Z^2, y = Y/Z^3, identity Z = 0  (ark_ec Projective)
+ *   field_id        ZK_FP = Pallas base / Vesta scalar field, ZK_FQ = Vesta base / Pallas scalar field
+ *   curve_id        ZK_PALLAS (coordinates Fp, scalars Fq), ZK_VESTA (coordinates Fq, scalars Fp)
+ *
+ * Every function returns 0 on success or a negative ZK_ERR_* code; zk_last_error() describes the last failure of
+ * the calling thread.  Nothing unwinds across the boundary.  A context serialises its own calls (the 15 concurrent
+ * rayon callers of kimchi/src/prover.rs:329-351 may share one context; use several contexts for concurrency).
+ * There is NO CPU fallback: without a CUDA device zk_ctx_create fails with ZK_ERR_NO_DEVICE.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define ZK_FP 0
+#define ZK_FQ 1
+#define ZK_PALLAS 0
+#define ZK_VESTA 1
+
+#define ZK_OK 0
+#define ZK_ERR_INVALID (-1)
+#define ZK_ERR_CUDA (-2)
+#define ZK_ERR_NO_DEVICE (-3)
+#define ZK_ERR_LENGTH (-4)
+
+typedef struct zk_ctx zk_ctx;       /* one CUDA device + stream + scratch; one per process/rank in multi-GPU runs */
+typedef struct zk_bases zk_bases;   /* a resident set of MSM bases (an SRS `g`, or one Lagrange basis) */
+typedef struct zk_srs zk_srs;       /* host-side mirror of poly_commitment::ipa::SRS<G> on top of the above */
+
+/* ------------------------------------------------------------------ library / context */
+const char* zk_last_error(void);
+int zk_device_count(void);
+int zk_ctx_create(int device_id, zk_ctx** out);
+void zk_ctx_destroy(zk_ctx* ctx);
+/* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream. */
+int zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream);
+/* Kernels launched by this context so far (bench.py's gpu_launches). */
+uint64_t zk_ctx_launch_count(const zk_ctx* ctx);
+/* Per-stage device timing with CUDA events on the launching stream (bench.py's roofline line).  After a profiled call
+ * zk_ctx_last_stage_ms fills out[0..5] = MSM stages {recode, scan, scatter, accumulate, segreduce, bitsum} of the last
+ * MSM and out[6] = all kernels of the last NTT call, in milliseconds.  capacity >= 8. */
+int zk_ctx_set_profile(zk_ctx* ctx, int enabled);
+int zk_ctx_last_stage_ms(const zk_ctx* ctx, float* out, size_t capacity);
+
+/* ------------------------------------------------------------------ resident bases
+ * Replaces holding `SRS::g: Vec<G>` / a cached Lagrange basis in host memory (poly-commitment/src/ipa.rs:56-75,780-795).
+ * window_bits: 0 = keep only the points (per-window buckets, host combines windows);
+ *              2..16 = also precompute T[w][i] = 2^(w*window_bits) * P_i so every MSM on these bases uses ONE bucket set;
+ *              -1 = pick the table window from n.
+ * points_on_device != 0: xy_mont is a device pointer. */
+int zk_bases_upload(zk_ctx* ctx, int curve_id, const uint64_t* xy_mont, size_t n, int window_bits, int points_on_device,
+                    zk_bases** out);
+void zk_bases_free(zk_bases* bases);
+size_t zk_bases_len(const zk_bases* bases);
+int zk_bases_window_bits(const zk_bases* bases);
+
+/* ------------------------------------------------------------------ MSM
+ * zk_msm == <G::Group as VariableBaseMSM>::msm_bigint(&bases[off..off+n], scalars)   (scalars_are_mont = 0: canonical
+ *           integers, poly-commitment/src/ipa.rs:672,943,953; commitment.rs:382,387)
+ *        == VariableBaseMSM::msm(...).unwrap()                                        (scalars_are_mont = 1: the
+ *           into_bigint conversion runs on the device, ipa.rs:649,658,659)
+ * window_bits: 0 = default; ignored when the bases carry a table.  out_xyz: Jacobian.
+ * The *_dev variant takes scalars already resident in device memory (n x 4 u64). */
+int zk_msm(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, int scalars_are_mont,
+           int window_bits, uint64_t out_xyz[12]);
+int zk_msm_dev(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* d_scalars, int scalars_are_mont,
+               int window_bits, uint64_t out_xyz[12]);
+/* k MSMs sharing the same bases slice (the chunks of t, the 15 witness columns): scalars k x n x 4, out k x 12. */
+int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, size_t k,
+                 int scalars_are_mont, int window_bits, uint64_t* out_xyz);
+/* Projective::into_affine / `+` on the host (result handling; multi-GPU partial sums after the all-gather). */
+int zk_jacobian_to_affine(int curve_id, const uint64_t xyz[12], uint64_t out_xy[8]);
+int zk_jacobian_add(int curve_id, const uint64_t a_xyz[12], const uint64_t b_xyz[12], uint64_t out_xyz[12]);
+int zk_jacobian_sum(int curve_id, const uint64_t* xyz, size_t count, uint64_t out_xyz[12]);
+
+/* ------------------------------------------------------------------ NTT
+ * == Radix2EvaluationDomain::<F>::new(1 << log_n).{fft_in_place, ifft_in_place}(data)
+ *    (coset != 0: the domain is get_coset(F::GENERATOR), i.e. coset_fft / coset_ifft)
+ * reached from Evaluations::interpolate / DensePolynomial::evaluate_over_domain at kimchi/src/prover.rs:289,377,907,1163,
+ * kimchi/src/circuits/constraints.rs:494, poly-commitment/src/utils.rs:195-198.
+ * data: batch polynomials of 2^log_n elements, back to back, transformed in place, natural order in and out.
+ * in_len: forward input length per polynomial (elements >= in_len are taken as zero, like ark's resize); 0 = full. */
+int zk_ntt(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, int inverse, int coset);
+int zk_ntt_batch(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, size_t batch, size_t in_len, int inverse,
+                 int coset);
+int zk_ntt_dev(zk_ctx* ctx, int field_id, void* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse,
+               int coset);
+
+/* ------------------------------------------------------------------ SRS mirror (poly-commitment/src/lib.rs:61-241, ipa.rs)
+ * zk_srs_create            SRS{g, h} with g resident on the device            (ipa.rs:56-75)
+ * zk_srs_max_poly_size     SRS::max_poly_size / size                           (ipa.rs:596-599, :798)
+ * zk_srs_add_lagrange_basis register the basis of a domain (cache entry of get_lagrange_basis, ipa.rs:780-795)
+ * zk_srs_commit_non_hiding SRS::commit_non_hiding(plnm, num_chunks)            (ipa.rs:638-683): coefficients in
+ *                          Montgomery form; writes max(ceil(len/|g|), num_chunks, 1) affine chunks, returns the count
+ * zk_srs_commit_evaluations_non_hiding  SRS::commit_evaluations_non_hiding     (ipa.rs:706-728): evals on a domain of
+ *                          evals_domain_size >= domain_size are sub-sampled; fails (ZK_ERR_INVALID) where the reference panics
+ * zk_srs_mask_custom       SRS::mask_custom: chunk_i + blinder_i * h           (ipa.rs:605-622); ZK_ERR_LENGTH ==
+ *                          CommitmentError::BlindersDontMatch (poly-commitment/src/error.rs:3-9) */
+int zk_srs_create(zk_ctx* ctx, int curve_id, const uint64_t* g_xy, size_t n, const uint64_t h_xy[8], int window_bits,
+                  zk_srs** out);
+void zk_srs_destroy(zk_srs* srs);
+size_t zk_srs_max_poly_size(const zk_srs* srs);
+int zk_srs_add_lagrange_basis(zk_srs* srs, size_t domain_size, const uint64_t* basis_xy, int window_bits);
+int zk_srs_commit_non_hiding(zk_srs* srs, const uint64_t* coeffs_mont, size_t len, size_t num_chunks, uint64_t* out_xy,
+                             size_t out_capacity, size_t* out_chunks);
+int zk_srs_commit_evaluations_non_hiding(zk_srs* srs, size_t domain_size, const uint64_t* evals_mont,
+                                         size_t evals_domain_size, uint64_t out_xy[8]);
+int zk_srs_mask_custom(zk_srs* srs, const uint64_t* chunks_xy, size_t n_chunks, const uint64_t* blinders_mont,
+                       size_t n_blinders, uint64_t* out_xy);
+
+/* ------------------------------------------------------------------ diagnostics (tests/test_gpu_field.py, DESIGN.md compute model)
+ * Element-wise device field ops on n elements (op: 0 mul, 1 add, 2 sub, 3 inverse of a), host pointers. */
+int zk_debug_field_op(zk_ctx* ctx, int field_id, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* Sustained Montgomery multiplications per second of the device (iters dependent fe_mul per thread, full grid). */
+int zk_debug_mul_throughput(zk_ctx* ctx, int field_id, unsigned iters, double* out_mul_per_s);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

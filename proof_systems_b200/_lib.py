@@ -1,0 +1,239 @@
+"""ctypes bindings of libzkb200.so (include/zkb200.h).  No fallback: a missing library is an ImportError."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+FP, FQ = 0, 1
+PALLAS, VESTA = 0, 1
+BASE_FIELD = {PALLAS: FP, VESTA: FQ}
+SCALAR_FIELD = {PALLAS: FQ, VESTA: FP}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libzkb200.so")
+
+
+def library_path() -> str:
+    return _SO
+
+
+class ZkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"zkb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library.  Raises ImportError if it was not built (python __graft_entry__.py / make -C csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise ImportError(
+            f"{_SO} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "proof_systems_b200 has no CPU fallback.")
+    L = ctypes.CDLL(_SO)
+    vp, sz, i, u = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint
+    L.zk_last_error.restype = ctypes.c_char_p
+    L.zk_device_count.restype = i
+    L.zk_ctx_create.argtypes = [i, ctypes.POINTER(vp)]
+    L.zk_ctx_destroy.argtypes = [vp]
+    L.zk_ctx_destroy.restype = None
+    L.zk_ctx_set_stream.argtypes = [vp, vp]
+    L.zk_ctx_launch_count.argtypes = [vp]
+    L.zk_ctx_launch_count.restype = ctypes.c_uint64
+    L.zk_ctx_set_profile.argtypes = [vp, i]
+    L.zk_ctx_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), sz]
+    L.zk_bases_upload.argtypes = [vp, i, vp, sz, i, i, ctypes.POINTER(vp)]
+    L.zk_bases_free.argtypes = [vp]
+    L.zk_bases_free.restype = None
+    L.zk_bases_len.argtypes = [vp]
+    L.zk_bases_len.restype = sz
+    L.zk_bases_window_bits.argtypes = [vp]
+    L.zk_msm.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
+    L.zk_msm_dev.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
+    L.zk_msm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i, i, _u64p]
+    L.zk_jacobian_to_affine.argtypes = [i, _u64p, _u64p]
+    L.zk_jacobian_add.argtypes = [i, _u64p, _u64p, _u64p]
+    L.zk_jacobian_sum.argtypes = [i, _u64p, sz, _u64p]
+    L.zk_ntt.argtypes = [vp, i, vp, u, i, i]
+    L.zk_ntt_batch.argtypes = [vp, i, vp, u, sz, sz, i, i]
+    L.zk_ntt_dev.argtypes = [vp, i, vp, u, sz, sz, i, i]
+    L.zk_srs_create.argtypes = [vp, i, vp, sz, _u64p, i, ctypes.POINTER(vp)]
+    L.zk_srs_destroy.argtypes = [vp]
+    L.zk_srs_destroy.restype = None
+    L.zk_srs_max_poly_size.argtypes = [vp]
+    L.zk_srs_max_poly_size.restype = sz
+    L.zk_srs_add_lagrange_basis.argtypes = [vp, sz, vp, i]
+    L.zk_srs_commit_non_hiding.argtypes = [vp, vp, sz, sz, _u64p, sz, ctypes.POINTER(sz)]
+    L.zk_srs_commit_evaluations_non_hiding.argtypes = [vp, sz, vp, sz, _u64p]
+    L.zk_srs_mask_custom.argtypes = [vp, vp, sz, vp, sz, _u64p]
+    L.zk_debug_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
+    L.zk_debug_mul_throughput.argtypes = [vp, i, u, ctypes.POINTER(ctypes.c_double)]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise ZkError(rc, lib().zk_last_error().decode(errors="replace"))
+
+
+def _np_u64(a, shape_tail):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.size % int(np.prod(shape_tail)) == 0
+    return a.reshape((-1,) + tuple(shape_tail))
+
+
+def _ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _out(n):
+    return np.empty(n, dtype=np.uint64)
+
+
+def jacobian_to_affine(curve: int, xyz) -> np.ndarray:
+    """Projective::into_affine()"""
+    xyz = np.ascontiguousarray(xyz, dtype=np.uint64)
+    out = _out(8)
+    check(lib().zk_jacobian_to_affine(curve, xyz.ctypes.data_as(_u64p), out.ctypes.data_as(_u64p)))
+    return out
+
+
+def jacobian_sum(curve: int, pts) -> np.ndarray:
+    pts = _np_u64(pts, (12,))
+    out = _out(12)
+    check(lib().zk_jacobian_sum(curve, pts.ctypes.data_as(_u64p), pts.shape[0], out.ctypes.data_as(_u64p)))
+    return out
+
+
+class Context:
+    """One CUDA device (one per process/rank)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        check(lib().zk_ctx_create(device, ctypes.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(lib().zk_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().zk_ctx_launch_count(self._h))
+
+    def set_profile(self, enabled: bool):
+        check(lib().zk_ctx_set_profile(self._h, int(enabled)))
+
+    def last_stage_ms(self) -> dict:
+        buf = (ctypes.c_float * 8)()
+        check(lib().zk_ctx_last_stage_ms(self._h, buf, 8))
+        names = ["recode", "scan", "scatter", "accumulate", "segreduce", "bitsum", "ntt"]
+        return {k: float(buf[i]) for i, k in enumerate(names)}
+
+    # ------------------------------------------------------------------ MSM
+    def upload_bases(self, curve: int, points, window_bits: int = -1) -> "Bases":
+        return Bases(self, curve, points, window_bits)
+
+    def msm(self, bases: "Bases", scalars, off: int = 0, mont: bool = False, window_bits: int = 0) -> np.ndarray:
+        """== G::Group::msm_bigint(&bases[off..off+n], scalars) (mont=False) / ::msm (mont=True).  Returns Jacobian [12]."""
+        sc = _np_u64(scalars, (4,))
+        out = _out(12)
+        check(lib().zk_msm(self._h, bases._h, off, sc.shape[0], _ptr(sc), int(mont), window_bits, out.ctypes.data_as(_u64p)))
+        return out
+
+    def msm_dev(self, bases: "Bases", d_scalars: int, n: int, off: int = 0, mont: bool = False, window_bits: int = 0) -> np.ndarray:
+        out = _out(12)
+        check(lib().zk_msm_dev(self._h, bases._h, off, n, ctypes.c_void_p(d_scalars), int(mont), window_bits, out.ctypes.data_as(_u64p)))
+        return out
+
+    def msm_batch(self, bases: "Bases", scalars, off: int = 0, mont: bool = False, window_bits: int = 0) -> np.ndarray:
+        """scalars [k, n, 4] -> Jacobian [k, 12]"""
+        sc = np.ascontiguousarray(scalars, dtype=np.uint64)
+        assert sc.ndim == 3 and sc.shape[2] == 4
+        k, n = sc.shape[0], sc.shape[1]
+        out = np.empty((k, 12), dtype=np.uint64)
+        check(lib().zk_msm_batch(self._h, bases._h, off, n, _ptr(sc), k, int(mont), window_bits, out.ctypes.data_as(_u64p)))
+        return out
+
+    def msm_affine(self, bases: "Bases", scalars, **kw) -> np.ndarray:
+        return jacobian_to_affine(bases.curve, self.msm(bases, scalars, **kw))
+
+    # ------------------------------------------------------------------ NTT
+    def ntt(self, field: int, data, inverse: bool = False, coset: bool = False, in_len: int = 0) -> np.ndarray:
+        """Transforms a copy.  data [n,4] or [batch,n,4] (Montgomery); n a power of two."""
+        a = np.array(data, dtype=np.uint64, order="C", copy=True)
+        assert a.shape[-1] == 4
+        n = a.shape[-2]
+        batch = 1 if a.ndim == 2 else a.shape[0]
+        log_n = n.bit_length() - 1
+        assert 1 << log_n == n
+        check(lib().zk_ntt_batch(self._h, field, _ptr(a), log_n, batch, in_len, int(inverse), int(coset)))
+        return a
+
+    def ntt_dev(self, field: int, d_data: int, log_n: int, batch: int = 1, in_len: int = 0, inverse: bool = False, coset: bool = False):
+        check(lib().zk_ntt_dev(self._h, field, ctypes.c_void_p(d_data), log_n, batch, in_len, int(inverse), int(coset)))
+
+    # ------------------------------------------------------------------ diagnostics
+    def field_op(self, field: int, op: str, a, b=None) -> np.ndarray:
+        a = _np_u64(a, (4,))
+        b = a if b is None else _np_u64(b, (4,))
+        out = np.empty_like(a)
+        code = {"mul": 0, "add": 1, "sub": 2, "inv": 3}[op]
+        check(lib().zk_debug_field_op(self._h, field, code, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out
+
+    def mul_throughput(self, field: int = FP, iters: int = 2000) -> float:
+        v = ctypes.c_double()
+        check(lib().zk_debug_mul_throughput(self._h, field, iters, ctypes.byref(v)))
+        return v.value
+
+
+class Bases:
+    """Resident MSM bases (SRS::g or one Lagrange basis) on the context's device."""
+
+    def __init__(self, ctx: Context, curve: int, points, window_bits: int = -1, device_ptr: int | None = None, n: int | None = None):
+        self.ctx, self.curve = ctx, curve
+        self._h = ctypes.c_void_p()
+        if device_ptr is not None:
+            check(lib().zk_bases_upload(ctx._h, curve, ctypes.c_void_p(device_ptr), n, window_bits, 1, ctypes.byref(self._h)))
+        else:
+            pts = _np_u64(points, (8,))
+            check(lib().zk_bases_upload(ctx._h, curve, _ptr(pts), pts.shape[0], window_bits, 0, ctypes.byref(self._h)))
+
+    def __len__(self):
+        return int(lib().zk_bases_len(self._h))
+
+    @property
+    def window_bits(self) -> int:
+        return int(lib().zk_bases_window_bits(self._h))
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib().zk_bases_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass

@@ -1,0 +1,403 @@
+// api.cu — the extern "C" boundary (include/zkb200.h): contexts, resident bases, MSM, NTT, diagnostics.
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/zkb200.h"
+#include "ctx.hpp"
+#include "host_field.hpp"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace zkb {
+
+static thread_local char g_err[512] = "";
+void zk_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------- host tail of the MSM
+template <class HP> static host::hxyzz msm_finish_t(const xyzz_t* T, unsigned c, unsigned G) {
+    using namespace host;
+    static_assert(sizeof(hxyzz) == sizeof(xyzz_t), "layout");
+    hxyzz total = identity();
+    for (int g = (int)G - 1; g >= 0; g--) {
+        if (g != (int)G - 1)
+            for (unsigned k = 0; k < c; k++) total = pdbl<HP>(total);
+        hxyzz acc = identity();
+        for (int t = (int)c - 1; t >= 0; t--) {
+            hxyzz tt;
+            memcpy(&tt, T + (size_t)g * c + t, sizeof tt);
+            acc = padd<HP>(pdbl<HP>(acc), tt);
+        }
+        total = padd<HP>(total, acc);
+    }
+    return total;
+}
+
+static void xyzz_to_jac_out(int curve, const host::hxyzz& p, uint64_t out[12]) {
+    host::hjac j = curve == ZK_PALLAS ? host::to_jacobian<host::HFp>(p) : host::to_jacobian<host::HFq>(p);
+    memcpy(out, &j, sizeof j);
+}
+
+int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* d_scalars, int mont, int window_bits,
+                   uint64_t out_xyz[12]) {
+    if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
+    MsmResultShape shape;
+    unsigned nl = 0;
+    int rc;
+    if (bases->b.curve == ZK_PALLAS)
+        rc = msm_run<FpParams, FqParams>(bases->b, off, n, d_scalars, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
+    else
+        rc = msm_run<FqParams, FpParams>(bases->b, off, n, d_scalars, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
+    if (rc) return rc;
+    ctx->launches += nl;
+    host::hxyzz r = host::identity();
+    if (shape.groups) {
+        r = bases->b.curve == ZK_PALLAS ? msm_finish_t<host::HFp>(ctx->ws.h_bitsums, shape.c, shape.groups)
+                                        : msm_finish_t<host::HFq>(ctx->ws.h_bitsums, shape.c, shape.groups);
+    }
+    xyzz_to_jac_out(bases->b.curve, r, out_xyz);
+    return ZK_OK;
+}
+
+int ctx_ensure(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return ZK_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    ZK_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return ZK_OK;
+}
+
+static int ctx_ntt_tables(zk_ctx* ctx, int field, unsigned log_n, bool inverse, const fe** small, const NttTables** tabs) {
+    fe*& sm = ctx->ntt_small[field][inverse ? 1 : 0];
+    if (!sm) {
+        ZK_CUDA(cudaMalloc(&sm, 512 * sizeof(fe)));
+        int rc = field == ZK_FP ? ntt_build_small_table<FpParams>(sm, inverse, ctx->stream) : ntt_build_small_table<FqParams>(sm, inverse, ctx->stream);
+        if (rc) return rc;
+        ctx->launches += 2;
+    }
+    unsigned key = (unsigned)field | (inverse ? 2u : 0u) | (log_n << 2);
+    auto it = ctx->ntt_tables.find(key);
+    if (it == ctx->ntt_tables.end()) {
+        NttTables t;
+        int rc = field == ZK_FP ? ntt_build_tables<FpParams>(t, log_n, inverse, ctx->stream) : ntt_build_tables<FqParams>(t, log_n, inverse, ctx->stream);
+        if (rc) return rc;
+        ctx->launches += 5;
+        it = ctx->ntt_tables.emplace(key, t).first;
+    }
+    *small = sm;
+    *tabs = &it->second;
+    return ZK_OK;
+}
+
+static int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
+    if (field != ZK_FP && field != ZK_FQ) { zk_set_error("ntt: unknown field_id %d", field); return ZK_ERR_INVALID; }
+    if (log_n > NTT_MAX_LOG_N) { zk_set_error("ntt: log_n %u > %u not supported", log_n, NTT_MAX_LOG_N); return ZK_ERR_INVALID; }
+    const fe* small;
+    const NttTables* tabs;
+    int rc = ctx_ntt_tables(ctx, field, log_n, inverse != 0, &small, &tabs);
+    if (rc) return rc;
+    size_t bytes = ((size_t)batch << log_n) * sizeof(fe);
+    fe* tmp = nullptr;
+    if (log_n > NTT_MAX_LOG_SUB) {
+        rc = ctx_ensure((void**)&ctx->d_ntt_tmp, &ctx->cap_ntt_tmp, bytes);
+        if (rc) return rc;
+        tmp = ctx->d_ntt_tmp;
+    }
+    unsigned nl = 0;
+    if (ctx->profile) {
+        if (!ctx->ev_ntt[0]) { ZK_CUDA(cudaEventCreate(&ctx->ev_ntt[0])); ZK_CUDA(cudaEventCreate(&ctx->ev_ntt[1])); }
+        ZK_CUDA(cudaEventRecord(ctx->ev_ntt[0], ctx->stream));
+    }
+    rc = field == ZK_FP ? ntt_run<FpParams>(d_data, tmp, small, *tabs, log_n, batch, in_len, inverse != 0, coset != 0, ctx->stream, &nl)
+                        : ntt_run<FqParams>(d_data, tmp, small, *tabs, log_n, batch, in_len, inverse != 0, coset != 0, ctx->stream, &nl);
+    ctx->launches += nl;
+    if (rc == ZK_OK && ctx->profile) {
+        ZK_CUDA(cudaEventRecord(ctx->ev_ntt[1], ctx->stream));
+        ZK_CUDA(cudaEventSynchronize(ctx->ev_ntt[1]));
+        ZK_CUDA(cudaEventElapsedTime(&ctx->ntt_ms, ctx->ev_ntt[0], ctx->ev_ntt[1]));
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- diagnostics kernels
+template <class F> __global__ void k_field_op(int op, const fe* a, const fe* b, fe* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = load_fe(a + i), y = load_fe(b + i), r;
+    if (op == 0) r = fe_mul<F>(x, y);
+    else if (op == 1) r = fe_add<F>(x, y);
+    else if (op == 2) r = fe_sub<F>(x, y);
+    else r = fe_inv<F>(x);
+    store_fe(out + i, r);
+}
+template <class F> __global__ void k_mul_chain(fe* out, unsigned iters) {
+    fe x = fe_one<F>(), y = fe_r2<F>();
+    x.v[0] ^= threadIdx.x;
+    y.v[1] ^= blockIdx.x;
+    for (unsigned i = 0; i < iters; i++) {
+        x = fe_mul<F>(x, y);
+        y = fe_mul<F>(y, x);
+    }
+    if (x.v[0] == 0x12345678u && y.v[7] == 0x9abcdef0u) store_fe(out, x);  // keep the chain alive
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+// ============================================================================================== extern "C"
+extern "C" {
+
+const char* zk_last_error(void) { return g_err; }
+
+int zk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int zk_ctx_create(int device_id, zk_ctx** out) {
+    if (!out) { zk_set_error("ctx_create: out is null"); return ZK_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        zk_set_error("no CUDA device (%s): this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return ZK_ERR_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= n) { zk_set_error("ctx_create: device %d outside [0, %d)", device_id, n); return ZK_ERR_INVALID; }
+    ZK_CUDA(cudaSetDevice(device_id));
+    zk_ctx* ctx = new zk_ctx();
+    ctx->device = device_id;
+    cudaError_t se = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) { zk_set_error("cudaStreamCreate: %s", cudaGetErrorString(se)); delete ctx; return ZK_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return ZK_OK;
+}
+
+void zk_ctx_destroy(zk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    msm_workspace_free(ctx->ws);
+    if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    if (ctx->d_ntt) cudaFree(ctx->d_ntt);
+    if (ctx->d_ntt_tmp) cudaFree(ctx->d_ntt_tmp);
+    for (int f = 0; f < 2; f++) for (int d = 0; d < 2; d++) if (ctx->ntt_small[f][d]) cudaFree(ctx->ntt_small[f][d]);
+    for (auto& kv : ctx->ntt_tables) ntt_free_tables(kv.second);
+    for (auto& e : ctx->ev_ntt) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream) {
+    if (!ctx) { zk_set_error("set_stream: ctx is null"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ZK_OK;
+}
+
+uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zk_ctx_set_profile(zk_ctx* ctx, int enabled) {
+    if (!ctx) { zk_set_error("set_profile: ctx is null"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->ws.profile = enabled != 0;
+    ctx->profile = enabled != 0;
+    return ZK_OK;
+}
+
+int zk_ctx_last_stage_ms(const zk_ctx* ctx, float* out, size_t capacity) {
+    if (!ctx || !out || capacity < 8) { zk_set_error("last_stage_ms: need room for 8 floats"); return ZK_ERR_INVALID; }
+    for (int k = 0; k < 6; k++) out[k] = ctx->ws.stage_ms[k];
+    out[6] = ctx->ntt_ms;
+    out[7] = 0;
+    return ZK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- bases
+int zk_bases_upload(zk_ctx* ctx, int curve_id, const uint64_t* xy_mont, size_t n, int window_bits, int points_on_device, zk_bases** out) {
+    if (!ctx || !out || (!xy_mont && n)) { zk_set_error("bases_upload: null argument"); return ZK_ERR_INVALID; }
+    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("bases_upload: unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
+    if (window_bits < -1 || window_bits == 1 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("bases_upload: window_bits %d not in {-1, 0, 2..%u}", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    unsigned c = window_bits < 0 ? (unsigned)msm_default_window(n, true) : (unsigned)window_bits;
+    zk_bases* bs = new zk_bases();
+    bs->ctx = ctx;
+    bs->b.curve = curve_id;
+    int rc = curve_id == ZK_PALLAS ? msm_bases_create<FpParams>(bs->b, (const affine_t*)xy_mont, points_on_device != 0, n, c, ctx->stream)
+                                   : msm_bases_create<FqParams>(bs->b, (const affine_t*)xy_mont, points_on_device != 0, n, c, ctx->stream);
+    if (rc) { msm_bases_free(bs->b); delete bs; return rc; }
+    if (c) ctx->launches += 1;
+    *out = bs;
+    return ZK_OK;
+}
+
+void zk_bases_free(zk_bases* bases) {
+    if (!bases) return;
+    std::lock_guard<std::mutex> lk(bases->ctx->mu);
+    cudaSetDevice(bases->ctx->device);
+    msm_bases_free(bases->b);
+    delete bases;
+}
+
+size_t zk_bases_len(const zk_bases* bases) { return bases ? bases->b.n : 0; }
+int zk_bases_window_bits(const zk_bases* bases) { return bases ? (int)bases->b.c : 0; }
+
+// ---------------------------------------------------------------------------------------------- MSM
+int zk_msm_dev(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* d_scalars, int scalars_are_mont, int window_bits, uint64_t out_xyz[12]) {
+    if (!ctx || !bases || !out_xyz || (!d_scalars && n)) { zk_set_error("msm: null argument"); return ZK_ERR_INVALID; }
+    if (bases->ctx != ctx) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    return ctx_msm_device(ctx, bases, off, n, (const fe*)d_scalars, scalars_are_mont, window_bits, out_xyz);
+}
+
+int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, size_t k, int scalars_are_mont, int window_bits, uint64_t* out_xyz) {
+    if (!ctx || !bases || (!out_xyz && k) || (!scalars && n && k)) { zk_set_error("msm: null argument"); return ZK_ERR_INVALID; }
+    if (bases->ctx != ctx) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (k == 0) return ZK_OK;
+    int rc = ctx_ensure((void**)&ctx->d_scalars, &ctx->cap_scalars, std::max<size_t>(k * n, 1) * sizeof(fe));
+    if (rc) return rc;
+    if (n) ZK_CUDA(cudaMemcpyAsync(ctx->d_scalars, scalars, k * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t j = 0; j < k; j++) {
+        rc = ctx_msm_device(ctx, bases, off, n, ctx->d_scalars + j * n, scalars_are_mont, window_bits, out_xyz + 12 * j);
+        if (rc) return rc;
+    }
+    return ZK_OK;
+}
+
+int zk_msm(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, int scalars_are_mont, int window_bits, uint64_t out_xyz[12]) {
+    return zk_msm_batch(ctx, bases, off, n, scalars, 1, scalars_are_mont, window_bits, out_xyz);
+}
+
+static int check_curve(int curve_id) {
+    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
+    return ZK_OK;
+}
+
+int zk_jacobian_to_affine(int curve_id, const uint64_t xyz[12], uint64_t out_xy[8]) {
+    if (!xyz || !out_xy) { zk_set_error("null argument"); return ZK_ERR_INVALID; }
+    if (int rc = check_curve(curve_id)) return rc;
+    host::hjac j;
+    memcpy(&j, xyz, sizeof j);
+    host::haffine a = curve_id == ZK_PALLAS ? host::to_affine<host::HFp>(host::from_jacobian<host::HFp>(j))
+                                            : host::to_affine<host::HFq>(host::from_jacobian<host::HFq>(j));
+    memcpy(out_xy, &a, sizeof a);
+    return ZK_OK;
+}
+
+int zk_jacobian_sum(int curve_id, const uint64_t* xyz, size_t count, uint64_t out_xyz[12]) {
+    if ((!xyz && count) || !out_xyz) { zk_set_error("null argument"); return ZK_ERR_INVALID; }
+    if (int rc = check_curve(curve_id)) return rc;
+    host::hxyzz acc = host::identity();
+    for (size_t i = 0; i < count; i++) {
+        host::hjac j;
+        memcpy(&j, xyz + 12 * i, sizeof j);
+        acc = curve_id == ZK_PALLAS ? host::padd<host::HFp>(acc, host::from_jacobian<host::HFp>(j))
+                                    : host::padd<host::HFq>(acc, host::from_jacobian<host::HFq>(j));
+    }
+    xyzz_to_jac_out(curve_id, acc, out_xyz);
+    return ZK_OK;
+}
+
+int zk_jacobian_add(int curve_id, const uint64_t a_xyz[12], const uint64_t b_xyz[12], uint64_t out_xyz[12]) {
+    if (!a_xyz || !b_xyz || !out_xyz) { zk_set_error("null argument"); return ZK_ERR_INVALID; }
+    uint64_t both[24];
+    memcpy(both, a_xyz, 96);
+    memcpy(both + 12, b_xyz, 96);
+    return zk_jacobian_sum(curve_id, both, 2, out_xyz);
+}
+
+// ---------------------------------------------------------------------------------------------- NTT
+int zk_ntt_dev(zk_ctx* ctx, int field_id, void* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
+    if (!ctx || (!d_data && batch)) { zk_set_error("ntt: null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    return ctx_ntt_device(ctx, field_id, (fe*)d_data, log_n, batch, in_len, inverse, coset);
+}
+
+int zk_ntt_batch(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
+    if (!ctx || (!data && batch)) { zk_set_error("ntt: null argument"); return ZK_ERR_INVALID; }
+    if (log_n > NTT_MAX_LOG_N) { zk_set_error("ntt: log_n %u > %u not supported", log_n, NTT_MAX_LOG_N); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (batch == 0) return ZK_OK;
+    size_t bytes = ((size_t)batch << log_n) * sizeof(fe);
+    int rc = ctx_ensure((void**)&ctx->d_ntt, &ctx->cap_ntt, bytes);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(ctx->d_ntt, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ctx_ntt_device(ctx, field_id, ctx->d_ntt, log_n, batch, in_len, inverse, coset);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(data, ctx->d_ntt, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+int zk_ntt(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, int inverse, int coset) {
+    return zk_ntt_batch(ctx, field_id, data, log_n, 1, 0, inverse, coset);
+}
+
+// ---------------------------------------------------------------------------------------------- diagnostics
+int zk_debug_field_op(zk_ctx* ctx, int field_id, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    if (!ctx || !a || !b || !out) { zk_set_error("null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    fe *da, *db, *dout;
+    ZK_CUDA(cudaMalloc(&da, n * sizeof(fe)));
+    ZK_CUDA(cudaMalloc(&db, n * sizeof(fe)));
+    ZK_CUDA(cudaMalloc(&dout, n * sizeof(fe)));
+    ZK_CUDA(cudaMemcpyAsync(da, a, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(db, b, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (field_id == ZK_FP) k_field_op<FpParams><<<blocks, 128, 0, ctx->stream>>>(op, da, db, dout, n);
+    else k_field_op<FqParams><<<blocks, 128, 0, ctx->stream>>>(op, da, db, dout, n);
+    ZK_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    ZK_CUDA(cudaMemcpyAsync(out, dout, n * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return ZK_OK;
+}
+
+int zk_debug_mul_throughput(zk_ctx* ctx, int field_id, unsigned iters, double* out_mul_per_s) {
+    if (!ctx || !out_mul_per_s) { zk_set_error("null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    ZK_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    fe* dout;
+    ZK_CUDA(cudaMalloc(&dout, sizeof(fe)));
+    const unsigned blocks = prop.multiProcessorCount * 4, threads = 256;
+    cudaEvent_t e0, e1;
+    ZK_CUDA(cudaEventCreate(&e0));
+    ZK_CUDA(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {  // first launch warms up
+        ZK_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (field_id == ZK_FP) k_mul_chain<FpParams><<<blocks, threads, 0, ctx->stream>>>(dout, iters);
+        else k_mul_chain<FqParams><<<blocks, threads, 0, ctx->stream>>>(dout, iters);
+        ZK_CUDA(cudaEventRecord(e1, ctx->stream));
+        ZK_CUDA(cudaEventSynchronize(e1));
+    }
+    ctx->launches += 2;
+    float ms = 0;
+    ZK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *out_mul_per_s = 2.0 * iters * blocks * threads / (ms * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dout);
+    return ZK_OK;
+}
+
+}  // extern "C"

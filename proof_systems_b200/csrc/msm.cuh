@@ -1,0 +1,85 @@
+// msm.cuh — variable-base multi-scalar multiplication on Pallas / Vesta for sm_100a.
+//
+// Drop-in semantics of ark_ec::VariableBaseMSM::{msm_bigint, msm} as the reference calls them
+// (poly-commitment/src/ipa.rs:649-672,943,953,487,497; commitment.rs:382,387 — SURVEY.md §8 rows a1/a2):
+//     result = sum_i s_i * P_i       bases affine (x, y Montgomery; identity allowed), scalars canonical 255-bit
+// (or Montgomery, converted on the device first), min(len) semantics for msm_bigint.
+//
+// B200 shape (Pippenger with signed digits, bucket method):
+//   * resident bases: an SRS (or a Lagrange basis) is uploaded once and kept in HBM — optionally as a
+//     PRECOMPUTED table T[w][i] = 2^(c*w) * P_i (nwin * n affine points; 64 MiB for n = 2^16, c = 16).  With the table
+//     all windows share ONE bucket set, so there is no per-window bucket reduction and no Horner doubling chain:
+//     180 GB of HBM buys away ~half of the serial tail.  Without a table (one-shot bases) there is one bucket set per
+//     window and the host combines the windows.
+//   * scalars are recoded to signed base-2^c digits in (-2^(c-1), 2^(c-1)]; (digit != 0) entries are counting-sorted by
+//     bucket (histogram -> scan -> scatter, all on device);
+//   * accumulation is a balanced segmented reduction over the SORTED entry list: every thread sums a fixed-size chunk
+//     of consecutive entries with XYZZ mixed additions, whole runs go straight to their bucket, runs cut by a chunk
+//     boundary go to a partial list that is reduced with warp-shuffle segmented scans, level by level.  Work per
+//     thread is identical whatever the scalar distribution (all points in one bucket — the kimchi witness columns,
+//     SURVEY.md §3.1 — costs the same as uniform scalars), and no atomics touch curve points;
+//   * bucket reduction sum_b (b+1) B_b is evaluated bit-sliced: T_t = sum of the buckets whose (b+1) has bit t set —
+//     c masked tree sums, fully parallel — and the host finishes with c doublings.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace zkb {
+
+constexpr unsigned MSM_MAX_WINDOW_BITS = 16;
+constexpr unsigned MSM_CHUNK = 16;           // sorted entries per thread in the accumulation kernel
+constexpr uint32_t MSM_KEY_EMPTY = 0xffffffffu;
+
+// A resident set of bases on one device.
+struct MsmBases {
+    int curve = 0;             // 0 Pallas, 1 Vesta
+    size_t n = 0;              // number of points
+    unsigned c = 0;            // window bits of the precomputed table (0: no table)
+    unsigned nwin = 0;         // windows in the table
+    affine_t* d_points = nullptr;  // [max(1,nwin)][n]  row w holds 2^(c*w) * P_i
+};
+
+// Growable device scratch of one context/device (sized for the largest call seen so far).
+struct MsmWorkspace {
+    size_t cap_entries = 0, cap_buckets = 0, cap_partials = 0;
+    int32_t* d_digits = nullptr;      // [nwin][n]
+    uint32_t* d_counts = nullptr;     // [G*B]     histogram, then running cursor
+    uint32_t* d_offsets = nullptr;    // [G*B + 1] exclusive scan
+    uint32_t* d_entries = nullptr;    // [M]  point index | sign << 31, sorted by bucket
+    uint32_t* d_keys = nullptr;       // [M]  bucket id of every sorted entry
+    xyzz_t* d_buckets = nullptr;      // [G*B]
+    uint32_t* d_pkeys[2] = {nullptr, nullptr};  // partial lists (ping-pong)
+    xyzz_t* d_ppts[2] = {nullptr, nullptr};
+    xyzz_t* d_bitsums = nullptr;      // [G][c][BITSUM_BLOCKS] then [G][c]
+    xyzz_t* h_bitsums = nullptr;      // pinned host copy of [G][c]
+    uint32_t* d_total = nullptr;      // [1] number of sorted entries
+    uint32_t* h_total = nullptr;      // pinned
+    bool profile = false;             // record an event after every stage
+    cudaEvent_t ev[8] = {};           // MSM_ST_COUNT + 1 stage boundaries
+    float stage_ms[8] = {};           // duration of each stage in the last profiled call
+};
+void msm_workspace_free(MsmWorkspace& ws);
+
+int msm_default_window(size_t n, bool precomputed);
+unsigned msm_num_windows(unsigned c);
+
+// Upload n affine points (host or device memory, 16 u32 each) and optionally build the window table.
+template <class F> int msm_bases_create(MsmBases& b, const affine_t* pts, bool pts_on_device, size_t n, unsigned c_table, cudaStream_t st);
+void msm_bases_free(MsmBases& b);
+
+// Optional per-stage device timing (CUDA events on the launching stream), filled when MsmWorkspace::profile is set.
+enum MsmStage { MSM_ST_RECODE = 0, MSM_ST_SCAN, MSM_ST_SCATTER, MSM_ST_ACCUMULATE, MSM_ST_SEGREDUCE, MSM_ST_BITSUM, MSM_ST_COUNT };
+
+// What msm_run leaves in ws.h_bitsums: groups x c XYZZ points T[g][t]; the MSM is sum_g 2^(c g) sum_t 2^t T[g][t].
+struct MsmResultShape {
+    unsigned c = 0, groups = 0;   // groups == 0: empty MSM (identity)
+};
+
+// One MSM over bases[off .. off+n).  d_scalars_in: n scalars already on the device (8 u32 each).  window c: 0 = default
+// (ignored when the bases carry a precomputed table).  Synchronises the stream; the O(c) tail is finished by the caller.
+template <class F, class FS>
+int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, bool scalars_mont, unsigned c, MsmWorkspace& ws,
+            cudaStream_t st, MsmResultShape* shape, unsigned* launches);
+
+}  // namespace zkb

@@ -1,0 +1,132 @@
+"""Host-side mirrors of the reference interfaces on the MSM/NTT path, over the C ABI (srs.cu holds the policy code).
+
+Names, argument meaning and error behaviour follow the reference so that the parity tests read like its own:
+  poly_commitment::SRS / ipa::SRS<G>                  poly-commitment/src/lib.rs:61-241, ipa.rs:56-75,596-800
+  poly_commitment::PolyComm<C>{chunks}                poly-commitment/src/commitment.rs:47-50
+  poly_commitment::error::CommitmentError             poly-commitment/src/error.rs:3-9
+  ark_poly::Radix2EvaluationDomain<F>                 used as `D` in kimchi/src/prover.rs:39-42, circuits/domains.rs:24-33
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import BASE_FIELD, SCALAR_FIELD, Context, ZkError, _np_u64, _ptr, _u64p, check, lib
+
+
+class BlindersDontMatch(ValueError):
+    """CommitmentError::BlindersDontMatch(blinders_len, commitment_len)"""
+
+
+@dataclass
+class PolyComm:
+    """chunks: uint64 [k, 8] affine points (identity = zeros)"""
+    chunks: np.ndarray
+
+    def __len__(self):
+        return self.chunks.shape[0]
+
+
+class SRS:
+    """ipa::SRS<G>{g, h, lagrange_bases} with g (and every registered Lagrange basis) resident on the device."""
+
+    def __init__(self, ctx: Context, curve: int, g, h, window_bits: int = -1):
+        self.ctx, self.curve = ctx, curve
+        self.g = _np_u64(g, (8,))
+        self.h = np.ascontiguousarray(h, dtype=np.uint64).reshape(8)
+        self._h = ctypes.c_void_p()
+        check(lib().zk_srs_create(ctx._h, curve, _ptr(self.g), self.g.shape[0], self.h.ctypes.data_as(_u64p), window_bits, ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zk_srs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+    # fn max_poly_size(&self) -> usize  /  fn size(&self)
+    def max_poly_size(self) -> int:
+        return int(lib().zk_srs_max_poly_size(self._h))
+
+    size = max_poly_size
+
+    def blinding_commitment(self) -> np.ndarray:
+        return self.h
+
+    def add_lagrange_basis(self, domain_size: int, basis, window_bits: int = -1):
+        """Populate the cache behind get_lagrange_basis(domain) (ipa.rs:780-795) with a precomputed basis."""
+        b = _np_u64(basis, (8,))
+        assert b.shape[0] == domain_size
+        check(lib().zk_srs_add_lagrange_basis(self._h, domain_size, _ptr(b), window_bits))
+
+    # fn commit_non_hiding(&self, plnm: &DensePolynomial<F>, num_chunks: usize) -> PolyComm<G>
+    def commit_non_hiding(self, coeffs, num_chunks: int) -> PolyComm:
+        c = _np_u64(coeffs, (4,)) if len(coeffs) else np.zeros((0, 4), dtype=np.uint64)
+        cap = max(num_chunks, (c.shape[0] + self.g.shape[0] - 1) // self.g.shape[0], 1)
+        out = np.zeros((cap, 8), dtype=np.uint64)
+        k = ctypes.c_size_t()
+        check(lib().zk_srs_commit_non_hiding(self._h, _ptr(c) if c.size else None, c.shape[0], num_chunks,
+                                             out.ctypes.data_as(_u64p), cap, ctypes.byref(k)))
+        return PolyComm(out[: k.value])
+
+    # fn commit_evaluations_non_hiding(&self, domain: D<F>, plnm: &Evaluations<F, D<F>>) -> PolyComm<G>
+    def commit_evaluations_non_hiding(self, domain_size: int, evals) -> PolyComm:
+        e = _np_u64(evals, (4,))
+        out = np.zeros((1, 8), dtype=np.uint64)
+        check(lib().zk_srs_commit_evaluations_non_hiding(self._h, domain_size, _ptr(e), e.shape[0], out.ctypes.data_as(_u64p)))
+        return PolyComm(out)
+
+    # fn mask_custom(&self, com: PolyComm<G>, blinders: &PolyComm<F>) -> Result<BlindedCommitment<G>, CommitmentError>
+    def mask_custom(self, com: PolyComm, blinders) -> PolyComm:
+        b = _np_u64(blinders, (4,))
+        out = np.zeros_like(com.chunks)
+        try:
+            check(lib().zk_srs_mask_custom(self._h, _ptr(com.chunks), len(com), _ptr(b), b.shape[0], out.ctypes.data_as(_u64p)))
+        except ZkError as e:
+            if e.code == -4:
+                raise BlindersDontMatch(b.shape[0], len(com)) from e
+            raise
+        return PolyComm(out)
+
+    def commit_custom(self, coeffs, num_chunks: int, blinders) -> PolyComm:
+        return self.mask_custom(self.commit_non_hiding(coeffs, num_chunks), blinders)
+
+    def commit_evaluations_custom(self, domain_size: int, evals, blinders) -> PolyComm:
+        return self.mask_custom(self.commit_evaluations_non_hiding(domain_size, evals), blinders)
+
+
+class Radix2EvaluationDomain:
+    """ark_poly::Radix2EvaluationDomain::<F>::new(size) on the device.  `field` is ZK_FP or ZK_FQ."""
+
+    def __init__(self, ctx: Context, field: int, size: int):
+        if size <= 0:
+            raise ValueError("domain size must be positive")
+        log_n = (size - 1).bit_length()  # new(n) rounds up to the next power of two
+        self.ctx, self.field, self.log_size_of_group, self.size = ctx, field, log_n, 1 << log_n
+
+    def _run(self, a, inverse, coset):
+        a = _np_u64(a, (4,))
+        if a.shape[0] > self.size:
+            raise ValueError("more coefficients than the domain size")  # ark reduces mod X^n - 1; callers on the path never do
+        buf = np.zeros((self.size, 4), dtype=np.uint64)
+        buf[: a.shape[0]] = a
+        return self.ctx.ntt(self.field, buf, inverse=inverse, coset=coset, in_len=a.shape[0] if not inverse else 0)
+
+    def fft(self, coeffs) -> np.ndarray:
+        return self._run(coeffs, False, False)
+
+    def ifft(self, evals) -> np.ndarray:
+        return self._run(evals, True, False)
+
+    def coset_fft(self, coeffs) -> np.ndarray:
+        return self._run(coeffs, False, True)
+
+    def coset_ifft(self, evals) -> np.ndarray:
+        return self._run(evals, True, True)

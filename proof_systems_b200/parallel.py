@@ -1,0 +1,35 @@
+"""Multi-GPU MSM: the one exchange step of the path.
+
+sum_i s_i P_i shards by points (the reference does the same on CPU with rayon::join,
+poly-commitment/src/ipa.rs:652-662): every rank runs the full Pippenger on its slice and ends with one Jacobian point
+(96 bytes).  NCCL has no user-defined reduction, so the final point-sum is ONE all_gather of world x 96 bytes over
+NVLink followed by world-1 point additions on every rank (result replicated, identical bits on all ranks).
+The message is latency-bound (~10 us); there is nothing to overlap or fuse with the kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import jacobian_sum
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous slice [lo, hi) of the n points owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_point_sum(curve: int, partial_xyz: np.ndarray, group=None, device: torch.device | None = None) -> np.ndarray:
+    """Sum the per-rank Jacobian partials.  Works on any backend: pass device=cuda for NCCL, leave None for gloo."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return np.ascontiguousarray(partial_xyz, dtype=np.uint64).reshape(12)
+    world = dist.get_world_size(group)
+    mine = torch.from_numpy(np.ascontiguousarray(partial_xyz, dtype=np.uint64).view(np.int64).reshape(1, 12))
+    if device is not None:
+        mine = mine.to(device)
+    gathered = torch.empty((world, 12), dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    return jacobian_sum(curve, gathered.cpu().numpy().view(np.uint64))

@@ -1,0 +1,67 @@
+// tests/host_math/host_math.cpp — compiles the DEVICE math headers (field.cuh, curve.cuh) for the host, where the
+// PTX carry-chain primitives are emulated instruction by instruction, so the exact mad.lo.cc/madc.hi.cc sequences
+// the GPU will execute can be checked against the CPU oracle on a machine without a GPU.  Test infrastructure only.
+#include <cstring>
+#include "../../proof_systems_b200/csrc/curve.cuh"
+using namespace zkb;
+
+template <class F> static void mul_(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    fe x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32);
+    fe z = fe_mul<F>(x, y); memcpy(r, z.v, 32);
+}
+#define BIN(name, fn)                                                                                   \
+    extern "C" void hm_##name(int fid, const uint32_t* a, const uint32_t* b, uint32_t* r, size_t n) {   \
+        for (size_t i = 0; i < n; i++) {                                                                \
+            fe x, y; memcpy(x.v, a + 8 * i, 32); memcpy(y.v, b + 8 * i, 32);                            \
+            fe z = fid == 0 ? fn<FpParams>(x, y) : fn<FqParams>(x, y);                                  \
+            memcpy(r + 8 * i, z.v, 32);                                                                 \
+        }                                                                                               \
+    }
+BIN(mul, fe_mul)
+BIN(add, fe_add)
+BIN(sub, fe_sub)
+#define UN(name, fn)                                                                       \
+    extern "C" void hm_##name(int fid, const uint32_t* a, uint32_t* r, size_t n) {         \
+        for (size_t i = 0; i < n; i++) {                                                   \
+            fe x; memcpy(x.v, a + 8 * i, 32);                                              \
+            fe z = fid == 0 ? fn<FpParams>(x) : fn<FqParams>(x);                           \
+            memcpy(r + 8 * i, z.v, 32);                                                    \
+        }                                                                                  \
+    }
+UN(neg, fe_neg)
+UN(inv, fe_inv)
+UN(to_mont, fe_to_mont)
+UN(from_mont, fe_from_mont)
+
+extern "C" void hm_consts(int fid, uint32_t* one, uint32_t* r2, uint32_t* root) {
+    for (int i = 0; i < 8; i++) {
+        one[i] = fid == 0 ? FpParams::R(i) : FqParams::R(i);
+        r2[i] = fid == 0 ? FpParams::R2(i) : FqParams::R2(i);
+        root[i] = fid == 0 ? FpParams::ROOT(i) : FqParams::ROOT(i);
+    }
+}
+
+// curve: cid 0 = Pallas (base Fp), 1 = Vesta (base Fq).  op: 0 madd(p xyzz, q affine), 1 add(p, q xyzz), 2 dbl(p)
+// points: xyzz = 32 u32, affine = 16 u32.  Output always affine (16 u32) AND xyzz (32 u32).
+template <class F> static void curve_op_(int op, const uint32_t* p, const uint32_t* q, uint32_t* out_aff, uint32_t* out_xyzz) {
+    xyzz_t P, R; memcpy(&P, p, sizeof P);
+    if (op == 0) { affine_t Q; memcpy(&Q, q, sizeof Q); R = xyzz_madd<F>(P, Q); }
+    else if (op == 1) { xyzz_t Q; memcpy(&Q, q, sizeof Q); R = xyzz_add<F>(P, Q); }
+    else R = xyzz_dbl<F>(P);
+    affine_t A = xyzz_to_affine<F>(R);
+    memcpy(out_aff, &A, sizeof A); memcpy(out_xyzz, &R, sizeof R);
+}
+extern "C" void hm_curve_op(int cid, int op, const uint32_t* p, const uint32_t* q, uint32_t* out_aff, uint32_t* out_xyzz) {
+    if (cid == 0) curve_op_<FpParams>(op, p, q, out_aff, out_xyzz);
+    else curve_op_<FqParams>(op, p, q, out_aff, out_xyzz);
+}
+// sum of n affine points through repeated madd, result affine
+extern "C" void hm_sum_affine(int cid, const uint32_t* pts, size_t n, uint32_t* out_aff) {
+    xyzz_t acc = xyzz_identity();
+    for (size_t i = 0; i < n; i++) {
+        affine_t Q; memcpy(&Q, pts + 16 * i, sizeof Q);
+        acc = cid == 0 ? xyzz_madd<FpParams>(acc, Q) : xyzz_madd<FqParams>(acc, Q);
+    }
+    affine_t A = cid == 0 ? xyzz_to_affine<FpParams>(acc) : xyzz_to_affine<FqParams>(acc);
+    memcpy(out_aff, &A, sizeof A);
+}

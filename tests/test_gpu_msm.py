@@ -1,0 +1,146 @@
+"""MSM parity: CUDA path (through the C ABI) vs the CPU oracle and vs the reference's golden vectors, bit-exact after
+into_affine() (SURVEY.md "Hard parts": results are compared as canonical affine values)."""
+import numpy as np
+import pytest
+
+import proof_systems_b200 as zk
+
+pytestmark = pytest.mark.gpu
+
+PALLAS_GY = 12418654782883325593414442427049395787963493412651469444558597405572177144507
+VESTA_GY = 11426906929455361843568202299992114520848200991084027513389447476559454104162
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+def lagrange_scalars(orc, fid, n, i):
+    m = orc.MODULUS[fid]
+    log_n = n.bit_length() - 1
+    w = orc.fe_int(fid, orc.root_of_unity(fid, log_n))
+    wi = pow(w, -i, m) if n > 1 else 1
+    out, cur = [], pow(n, -1, m)
+    for _ in range(n):
+        out.append(cur)
+        cur = cur * wi % m
+    return orc.ints_to_limbs(out)
+
+
+def test_vesta_msm_kat(ctx, orc):
+    """kimchi/src/proof.rs:1163-1204"""
+    cid = orc.VESTA
+    G = np.concatenate([orc.fe(orc.FQ, 1), orc.fe(orc.FQ, VESTA_GY)])
+    basis = np.stack([orc.scalar_mul(cid, G, i) for i in range(1, 17)])
+    coeffs = [1, 7, 5, 35, 3, 21, 15, 105, 2, 14, 10, 70, 6, 42, 30, 210]   # b_poly_coefficients([2,3,5,7]), commitment.rs:869-910
+    sc = orc.ints_to_limbs(coeffs)
+    ex = 3756288960823668761746459900985719106126835112055076922409498125279524024429
+    ey = 7540929664328976141648477194277016811781677917189411360504995258251130097840
+    for wb in (0, 4, -1):
+        bases = ctx.upload_bases(cid, basis, window_bits=wb)
+        r = ctx.msm_affine(bases, sc)
+        assert orc.fe_int(orc.FQ, r[:4]) == ex and orc.fe_int(orc.FQ, r[4:]) == ey, wb
+        r = ctx.msm_affine(bases, orc.to_mont(orc.FP, sc), mont=True)       # VariableBaseMSM::msm takes field elements
+        assert orc.fe_int(orc.FQ, r[:4]) == ex, wb
+        bases.free()
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_config1_lagrange_2048_pinned_msms(ctx, orc, request, name):
+    """BASELINE config 1: 2^11-point MSMs against srs/test_*.srs; the answers are stored in the reference's file."""
+    srs = request.getfixturevalue(name)
+    want = srs.mont_points(srs.lag_2048_canon)
+    for wb in (0, 8, 13):
+        bases = ctx.upload_bases(srs.cid, srs.g[:2048], window_bits=wb)
+        for i in [0, 1, 2, 1000, 2047]:
+            sc = lagrange_scalars(orc, srs.scalar, 2048, i)
+            assert np.array_equal(ctx.msm_affine(bases, sc), want[i]), (wb, i)
+        rnd = orc.random_scalars(srs.scalar, 2048, seed=0)
+        assert np.array_equal(ctx.msm_affine(bases, rnd), orc.msm(srs.cid, srs.g[:2048], rnd)), wb
+        bases.free()
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_edge_cases_vs_oracle(ctx, orc, request, name):
+    """SURVEY.md §8d edge set: scalars 0, 1, r-1, 2^k; repeated bases (doubling); P and -P in one bucket; identity bases
+    (ipa.rs:848-850); n = 1 and n not a power of two (ipa.rs:648-651); sub-slices of the resident bases."""
+    srs = request.getfixturevalue(name)
+    cid = srs.cid
+    r = orc.MODULUS[srs.scalar]
+    g = srs.g[:100].copy()
+    g[5] = g[4]
+    g[7] = g[6]
+    g[7, 4:] = orc.fe_sub(srs.base, np.zeros(4, dtype=np.uint64), g[6, 4:])
+    g[9] = 0
+    g[50:60] = g[49]                  # ten copies of one point
+    sc = orc.random_scalars(srs.scalar, 100, seed=3)
+    sc[0] = 0
+    sc[1] = orc.int_to_limbs(1)
+    sc[2] = orc.int_to_limbs(r - 1)
+    sc[3] = orc.int_to_limbs(1 << 200)
+    sc[4] = sc[5] = orc.int_to_limbs(12345)
+    sc[6] = sc[7] = orc.int_to_limbs(999)
+    sc[50:60] = orc.int_to_limbs(77)  # same bucket, same point: exercises the P == Q branch of the mixed addition
+    for wb in (0, 3, 6, 16):
+        bases = ctx.upload_bases(cid, g, window_bits=wb)
+        for n in [1, 2, 3, 7, 33, 64, 100]:
+            assert np.array_equal(ctx.msm_affine(bases, sc[:n]), orc.msm(cid, g[:n], sc[:n])), (wb, n)
+        # slice with an offset: msm(&g[off..off+n], ..)
+        assert np.array_equal(ctx.msm_affine(bases, sc[:40], off=30), orc.msm(cid, g[30:70], sc[:40])), wb
+        # explicit window choices on table-less bases
+        if wb == 0:
+            for c in (2, 5, 9, 13, 16):
+                assert np.array_equal(ctx.msm_affine(bases, sc, window_bits=c), orc.msm(cid, g, sc)), c
+        # all-zero scalars -> identity; empty MSM -> identity
+        assert not np.any(ctx.msm_affine(bases, np.zeros((8, 4), dtype=np.uint64)))
+        assert not np.any(ctx.msm_affine(bases, np.zeros((0, 4), dtype=np.uint64)))
+        bases.free()
+
+
+def test_degenerate_all_ones_witness_column(ctx, orc, pallas_srs):
+    """kimchi's witness columns are {1 x 65526, 0 x 7, random x 3}: every point lands in one bucket.
+    The balanced accumulation must handle it; the answer is the plain sum of the bases."""
+    srs = pallas_srs
+    n = 4096
+    sc = np.zeros((n, 4), dtype=np.uint64)
+    sc[:, 0] = 1
+    sc[-10:-3] = 0
+    sc[-3:] = orc.random_scalars(srs.scalar, 3, seed=1)
+    bases = ctx.upload_bases(srs.cid, srs.g[:n], window_bits=-1)
+    assert np.array_equal(ctx.msm_affine(bases, sc), orc.msm(srs.cid, srs.g[:n], sc))
+    bases.free()
+
+
+def test_config2_2_16_pallas(ctx, orc, pallas_srs):
+    """BASELINE config 2: 2^16-point Pallas MSM on the real SRS, w = 16 table and the tuned window; one answer is
+    pinned by srs/test_pallas.srs (lagrange_bases[65536][i]), the random-scalar answer by the oracle."""
+    srs = pallas_srs
+    n = 1 << 16
+    rnd = orc.random_scalars(srs.scalar, n, seed=1)
+    want_rnd = orc.msm(srs.cid, srs.g, rnd)
+    want_lag = srs.mont_points(srs.lag_65536_canon)
+    lag_sc = lagrange_scalars(orc, srs.scalar, n, int(srs.lag_65536_idx[1]))
+    for wb in (16, -1, 0):
+        bases = ctx.upload_bases(srs.cid, srs.g, window_bits=wb)
+        assert np.array_equal(ctx.msm_affine(bases, rnd), want_rnd), wb
+        assert np.array_equal(ctx.msm_affine(bases, lag_sc), want_lag[1]), wb
+        # linearity / split property (ipa.rs:652-662: msm(g[..n/2]) + msm(g[n/2..]) == msm(g))
+        lo = ctx.msm(bases, rnd[: n // 2])
+        hi = ctx.msm(bases, rnd[n // 2:], off=n // 2)
+        assert np.array_equal(zk.jacobian_to_affine(srs.cid, zk.jacobian_sum(srs.cid, np.stack([lo, hi]))), want_rnd), wb
+        bases.free()
+
+
+def test_batch_shares_bases(ctx, orc, vesta_srs):
+    """the 7 chunks of t (ipa.rs:663-676) / 15 witness columns: k scalar vectors against the same resident bases."""
+    srs = vesta_srs
+    n, k = 2048, 5
+    bases = ctx.upload_bases(srs.cid, srs.g[:n], window_bits=-1)
+    sc = orc.random_scalars(srs.scalar, n * k, seed=11).reshape(k, n, 4)
+    out = ctx.msm_batch(bases, sc)
+    for j in range(k):
+        assert np.array_equal(zk.jacobian_to_affine(srs.cid, out[j]), orc.msm(srs.cid, srs.g[:n], sc[j])), j
+    bases.free()

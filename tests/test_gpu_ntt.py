@@ -1,0 +1,103 @@
+"""NTT parity: CUDA path (through the C ABI) vs the CPU oracle, bit-exact, plus size-independent properties at the
+BASELINE sizes.  Mirrors what the reference checks about its FFTs (no numeric vectors; cross-checks):
+kimchi/src/lagrange_basis_evaluations.rs:274-375, poly-commitment/tests/ipa_commitment.rs:27-119."""
+import numpy as np
+import pytest
+
+import proof_systems_b200 as zk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8, 10, 11, 12, 13, 16])
+def test_forward_and_inverse_match_oracle(ctx, orc, fid, log_n):
+    n = 1 << log_n
+    a = orc.to_mont(fid, orc.random_scalars(fid, n, seed=40 + log_n))
+    assert np.array_equal(ctx.ntt(fid, a), orc.ntt(fid, a))
+    assert np.array_equal(ctx.ntt(fid, a, inverse=True), orc.ntt(fid, a, inverse=True))
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+@pytest.mark.parametrize("log_n", [4, 10, 14])
+def test_coset_transforms_match_oracle(ctx, orc, fid, log_n):
+    n = 1 << log_n
+    a = orc.to_mont(fid, orc.random_scalars(fid, n, seed=7))
+    assert np.array_equal(ctx.ntt(fid, a, coset=True), orc.ntt(fid, a, coset=True))
+    assert np.array_equal(ctx.ntt(fid, a, inverse=True, coset=True), orc.ntt(fid, a, inverse=True, coset=True))
+
+
+@pytest.mark.parametrize("log_n,batch", [(3, 5), (9, 15), (12, 3), (16, 2)])
+def test_batched_matches_per_polynomial(ctx, orc, log_n, batch):
+    """prover.rs:370-381 issues 15 independent iFFTs; the batch call must equal 15 single calls."""
+    fid = zk.FP
+    n = 1 << log_n
+    a = orc.to_mont(fid, orc.random_scalars(fid, n * batch, seed=3)).reshape(batch, n, 4)
+    got = ctx.ntt(fid, a, inverse=True)
+    for j in range(batch):
+        assert np.array_equal(got[j], orc.ntt(fid, a[j], inverse=True)), j
+
+
+@pytest.mark.parametrize("log_n,in_len", [(6, 8), (13, 1024), (16, 8192), (10, 1)])
+def test_zero_padded_input(ctx, orc, log_n, in_len):
+    """evaluate_over_domain of a short polynomial (constraints.rs:490-495: degree < n evaluated over d8)."""
+    fid = zk.FQ
+    n = 1 << log_n
+    coeffs = orc.to_mont(fid, orc.random_scalars(fid, in_len, seed=5))
+    padded = np.zeros((n, 4), dtype=np.uint64)
+    padded[:in_len] = coeffs
+    garbage = padded.copy()
+    garbage[in_len:] = orc.to_mont(fid, orc.random_scalars(fid, n - in_len, seed=6))   # must be ignored
+    assert np.array_equal(ctx.ntt(fid, garbage, in_len=in_len), orc.ntt(fid, padded))
+
+
+def test_radix2_domain_mirror(ctx, orc):
+    d = zk.Radix2EvaluationDomain(ctx, zk.FP, 1000)     # new(1000) -> size 1024
+    assert d.size == 1024 and d.log_size_of_group == 10
+    c = orc.to_mont(zk.FP, orc.random_scalars(zk.FP, 700, seed=8))
+    ev = d.fft(c)
+    padded = np.zeros((1024, 4), dtype=np.uint64)
+    padded[:700] = c
+    assert np.array_equal(ev, orc.ntt(zk.FP, padded))
+    assert np.array_equal(d.ifft(ev), padded)
+    assert np.array_equal(d.coset_ifft(d.coset_fft(c)), padded)
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+def test_config3_2_20_roundtrip_and_forward(ctx, orc, fid):
+    """BASELINE config 3: 2^20 elements, forward then inverse == input; forward == oracle; delta and linearity."""
+    log_n = 20
+    n = 1 << log_n
+    a = orc.to_mont(fid, orc.random_scalars(fid, n, seed=2))
+    f = ctx.ntt(fid, a)
+    assert np.array_equal(ctx.ntt(fid, f, inverse=True), a)
+    assert np.array_equal(f, orc.ntt(fid, a))
+    # linearity: NTT(a + b) = NTT(a) + NTT(b) on a sample of positions
+    b = orc.to_mont(fid, orc.random_scalars(fid, n, seed=9))
+    idx = [0, 1, 12345, n // 2, n - 1]
+    fb = ctx.ntt(fid, b)
+    ab = np.stack([orc.fe_add(fid, a[i], b[i]) for i in range(n)]) if False else None
+    s = a.copy()
+    # build a+b with the device op (already validated in test_gpu_field)
+    s = ctx.field_op(fid, "add", a, b)
+    fs = ctx.ntt(fid, s)
+    for i in idx:
+        assert np.array_equal(fs[i], orc.fe_add(fid, f[i], fb[i]))
+
+
+def test_domain_chain_d1_in_d8(ctx, orc):
+    """kimchi/src/circuits/domains.rs:64-66 + ipa.rs:717-722: evaluations over d8, sub-sampled by 8, are those over d1."""
+    fid = zk.FP
+    n = 1 << 12
+    c = orc.to_mont(fid, orc.random_scalars(fid, n, seed=12))
+    big = np.zeros((8 * n, 4), dtype=np.uint64)
+    big[:n] = c
+    ev8 = ctx.ntt(fid, big, in_len=n)
+    assert np.array_equal(ev8[::8], ctx.ntt(fid, c))

@@ -1,0 +1,95 @@
+"""The SRS mirror (proof_systems_b200.SRS over srs.cu) against the reference's contracts:
+  poly-commitment/src/pbt_srs.rs:21-85       chunk-count contract of commit_non_hiding
+  poly-commitment/tests/ipa_commitment.rs:27-119   interpolate+commit == commit_evaluations on the Lagrange basis
+  poly-commitment/src/ipa.rs:605-622,643-647       mask_custom, zero polynomial
+"""
+import numpy as np
+import pytest
+
+import proof_systems_b200 as zk
+from proof_systems_b200.host import BlindersDontMatch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_commit_non_hiding_expected_number_of_chunks(ctx, orc, request, name):
+    g = request.getfixturevalue(name)
+    rng = np.random.default_rng(7)
+    for log2_srs_size in (1, 3, 5):
+        n = 1 << log2_srs_size
+        srs = zk.SRS(ctx, g.cid, g.g[:n], g.mont_points(g.h_xy_canon)[0])
+        assert srs.max_poly_size() == n
+
+        def rand_poly(k):
+            return orc.to_mont(g.scalar, orc.random_scalars(g.scalar, k, seed=int(rng.integers(1 << 30))))
+
+        assert len(srs.commit_non_hiding(rand_poly(n), 1)) == 1
+        k = int(rng.integers(2, 10))
+        assert len(srs.commit_non_hiding(rand_poly(n), k)) == k
+        k = int(rng.integers(1, 10))
+        zero = srs.commit_non_hiding(np.zeros((0, 4), dtype=np.uint64), k)
+        assert len(zero) == k and not np.any(zero.chunks)                    # ipa.rs:643-647
+        k = int(rng.integers(2, 5))
+        p = rand_poly(k * n)
+        assert len(srs.commit_non_hiding(p, int(rng.integers(1, k)))) == k
+        assert len(srs.commit_non_hiding(p, k)) == k
+        req = int(rng.integers(k + 1, 10))
+        c = srs.commit_non_hiding(p, req)
+        assert len(c) == req and not np.any(c.chunks[k:])
+        # values: chunk j is the MSM of coefficient block j (incl. a ragged last block)
+        p2 = rand_poly(2 * n + max(1, n // 2))
+        c2 = srs.commit_non_hiding(p2, 1)
+        assert len(c2) == 3
+        for j in range(3):
+            blk = orc.from_mont(g.scalar, p2[j * n:(j + 1) * n])
+            assert np.array_equal(c2.chunks[j], orc.msm(g.cid, g.g[:len(blk)], blk)), j
+        srs.close()
+
+
+def test_commit_evaluations_equals_interpolate_then_commit(ctx, orc, pallas_srs):
+    """ipa_commitment.rs:27-119 (single-chunk case): <evals, lagrange_basis> == commit(interpolate(evals))."""
+    g = pallas_srs
+    n = 1 << 10
+    srs = zk.SRS(ctx, g.cid, g.g[:n], g.mont_points(g.h_xy_canon)[0])
+    srs.add_lagrange_basis(n, g.lagrange_small(n))          # the reference's stored basis for n = 1024
+    evals = orc.to_mont(g.scalar, orc.random_scalars(g.scalar, n, seed=21))
+    dom = zk.Radix2EvaluationDomain(ctx, g.scalar, n)
+    coeffs = dom.ifft(evals)
+    via_coeffs = srs.commit_non_hiding(coeffs, 1)
+    via_evals = srs.commit_evaluations_non_hiding(n, evals)
+    assert np.array_equal(via_coeffs.chunks, via_evals.chunks)
+    # evaluations living on a 4x larger domain are sub-sampled (ipa.rs:717-722)
+    big = np.zeros((4 * n, 4), dtype=np.uint64)
+    big[:n] = coeffs
+    evals4 = zk.Radix2EvaluationDomain(ctx, g.scalar, 4 * n).fft(big)
+    assert np.array_equal(srs.commit_evaluations_non_hiding(n, evals4).chunks, via_evals.chunks)
+    # the reference panics when the commitment domain is larger than the evaluation domain
+    with pytest.raises(zk.ZkError):
+        srs.commit_evaluations_non_hiding(n, evals[: n // 2])
+    srs.close()
+
+
+def test_mask_custom(ctx, orc, vesta_srs):
+    g = vesta_srs
+    n = 64
+    h = g.mont_points(g.h_xy_canon)[0]
+    srs = zk.SRS(ctx, g.cid, g.g[:n], h)
+    p = orc.to_mont(g.scalar, orc.random_scalars(g.scalar, 2 * n, seed=4))
+    com = srs.commit_non_hiding(p, 2)
+    bl_can = orc.random_scalars(g.scalar, 2, seed=5)
+    blinders = orc.to_mont(g.scalar, bl_can)
+    masked = srs.mask_custom(com, blinders)
+    for j in range(2):
+        want = orc.affine_add(g.cid, com.chunks[j], orc.scalar_mul(g.cid, h, orc.limbs_to_int(bl_can[j])))
+        assert np.array_equal(masked.chunks[j], want)
+    with pytest.raises(BlindersDontMatch):
+        srs.mask_custom(com, blinders[:1])
+    srs.close()
