@@ -134,6 +134,10 @@ int zk_srs_mask_custom(zk_srs* srs, const uint64_t* chunks_xy, size_t n_chunks, 
 int zk_debug_field_op(zk_ctx* ctx, int field_id, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* Sustained Montgomery multiplications per second of the device (iters dependent fe_mul per thread, full grid). */
 int zk_debug_mul_throughput(zk_ctx* ctx, int field_id, unsigned iters, double* out_mul_per_s);
+/* Latency/throughput probe: kind 1, 2, 4 = that many independent dependent-chains of fe_mul per thread, 100 = a chain
+ * of XYZZ mixed additions; blocks x threads grid (blocks 0 = 4 per SM); reports operations per second. */
+int zk_debug_op_throughput(zk_ctx* ctx, int field_id, int kind, unsigned blocks, unsigned threads, unsigned iters,
+                           double* out_ops_per_s);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

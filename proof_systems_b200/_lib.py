@@ -76,6 +76,7 @@ def lib() -> ctypes.CDLL:
     L.zk_srs_mask_custom.argtypes = [vp, vp, sz, vp, sz, _u64p]
     L.zk_debug_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.zk_debug_mul_throughput.argtypes = [vp, i, u, ctypes.POINTER(ctypes.c_double)]
+    L.zk_debug_op_throughput.argtypes = [vp, i, i, u, u, u, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
 
@@ -200,6 +201,11 @@ class Context:
         code = {"mul": 0, "add": 1, "sub": 2, "inv": 3}[op]
         check(lib().zk_debug_field_op(self._h, field, code, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
         return out
+
+    def op_throughput(self, kind: int, blocks: int, threads: int, iters: int = 500, field: int = FP) -> float:
+        v = ctypes.c_double()
+        check(lib().zk_debug_op_throughput(self._h, field, kind, blocks, threads, iters, ctypes.byref(v)))
+        return v.value
 
     def mul_throughput(self, field: int = FP, iters: int = 2000) -> float:
         v = ctypes.c_double()

@@ -139,15 +139,33 @@ template <class F> __global__ void k_field_op(int op, const fe* a, const fe* b, 
     else r = fe_inv<F>(x);
     store_fe(out + i, r);
 }
-template <class F> __global__ void k_mul_chain(fe* out, unsigned iters) {
-    fe x = fe_one<F>(), y = fe_r2<F>();
-    x.v[0] ^= threadIdx.x;
+// ILP independent dependent-chains of fe_mul per thread (ILP = 1, 2, 4): latency vs throughput probe
+template <class F, int ILP> __global__ void k_mul_chain(fe* out, unsigned iters) {
+    fe x[ILP], y = fe_r2<F>();
     y.v[1] ^= blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) { x[k] = fe_one<F>(); x[k].v[0] ^= threadIdx.x + 977 * k; }
     for (unsigned i = 0; i < iters; i++) {
-        x = fe_mul<F>(x, y);
-        y = fe_mul<F>(y, x);
+#pragma unroll
+        for (int k = 0; k < ILP; k++) x[k] = fe_mul<F>(x[k], y);
     }
-    if (x.v[0] == 0x12345678u && y.v[7] == 0x9abcdef0u) store_fe(out, x);  // keep the chain alive
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) acc ^= x[k].v[0] ^ x[k].v[7];
+    if (acc == 0x12345678u) store_fe(out, x[0]);  // keep the chains alive
+}
+// chain of XYZZ mixed additions (the MSM inner loop) on register-resident operands
+template <class F> __global__ void k_madd_chain(xyzz_t* out, unsigned iters) {
+    affine_t q;
+    q.x = fe_one<F>(); q.y = fe_r2<F>();
+    q.x.v[0] ^= threadIdx.x; q.y.v[1] ^= blockIdx.x;
+    xyzz_t acc = xyzz_from_affine<F>(q);
+    acc.X.v[2] ^= 0x55u;
+    for (unsigned i = 0; i < iters; i++) {
+        acc = xyzz_madd<F>(acc, q);
+        q.x.v[3] ^= acc.X.v[0];   // data-dependent operand so nothing is hoisted
+    }
+    if (acc.X.v[0] == 0x12345678u && acc.ZZ.v[7] == 0x9abcdef0u) store_xyzz(out, acc);
 }
 
 }  // namespace zkb
@@ -373,31 +391,44 @@ int zk_debug_field_op(zk_ctx* ctx, int field_id, int op, const uint64_t* a, cons
     return ZK_OK;
 }
 
-int zk_debug_mul_throughput(zk_ctx* ctx, int field_id, unsigned iters, double* out_mul_per_s) {
-    if (!ctx || !out_mul_per_s) { zk_set_error("null argument"); return ZK_ERR_INVALID; }
+// kind: 1, 2, 4 = fe_mul chains with that many independent chains per thread; 100 = xyzz_madd chain.
+// blocks == 0: 4 per SM.  Reports operations per second (fe_mul, or madd for kind 100).
+int zk_debug_op_throughput(zk_ctx* ctx, int field_id, int kind, unsigned blocks, unsigned threads, unsigned iters, double* out_ops_per_s) {
+    if (!ctx || !out_ops_per_s || threads == 0 || threads > 1024) { zk_set_error("op_throughput: bad argument"); return ZK_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
     ZK_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
-    fe* dout;
-    ZK_CUDA(cudaMalloc(&dout, sizeof(fe)));
-    const unsigned blocks = prop.multiProcessorCount * 4, threads = 256;
+    if (blocks == 0) blocks = prop.multiProcessorCount * 4;
+    xyzz_t* dout;
+    ZK_CUDA(cudaMalloc(&dout, sizeof(xyzz_t)));
     cudaEvent_t e0, e1;
     ZK_CUDA(cudaEventCreate(&e0));
     ZK_CUDA(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; rep++) {  // first launch warms up
         ZK_CUDA(cudaEventRecord(e0, ctx->stream));
-        if (field_id == ZK_FP) k_mul_chain<FpParams><<<blocks, threads, 0, ctx->stream>>>(dout, iters);
-        else k_mul_chain<FqParams><<<blocks, threads, 0, ctx->stream>>>(dout, iters);
+#define LAUNCH(F)                                                                                        \
+        if (kind == 1) k_mul_chain<F, 1><<<blocks, threads, 0, ctx->stream>>>((fe*)dout, iters);         \
+        else if (kind == 2) k_mul_chain<F, 2><<<blocks, threads, 0, ctx->stream>>>((fe*)dout, iters);    \
+        else if (kind == 4) k_mul_chain<F, 4><<<blocks, threads, 0, ctx->stream>>>((fe*)dout, iters);    \
+        else k_madd_chain<F><<<blocks, threads, 0, ctx->stream>>>(dout, iters);
+        if (field_id == ZK_FP) { LAUNCH(FpParams) } else { LAUNCH(FqParams) }
+#undef LAUNCH
+        ZK_CUDA(cudaGetLastError());
         ZK_CUDA(cudaEventRecord(e1, ctx->stream));
         ZK_CUDA(cudaEventSynchronize(e1));
     }
     ctx->launches += 2;
     float ms = 0;
     ZK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    *out_mul_per_s = 2.0 * iters * blocks * threads / (ms * 1e-3);
+    double per_thread = kind == 100 ? 1.0 : (double)kind;
+    *out_ops_per_s = per_thread * iters * (double)blocks * threads / (ms * 1e-3);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dout);
     return ZK_OK;
+}
+
+int zk_debug_mul_throughput(zk_ctx* ctx, int field_id, unsigned iters, double* out_mul_per_s) {
+    return zk_debug_op_throughput(ctx, field_id, 2, 0, 256, iters, out_mul_per_s);
 }
 
 }  // extern "C"

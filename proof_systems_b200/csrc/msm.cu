@@ -354,11 +354,15 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
         }
         if (ws.cap_partials < need_bits) {
             if (ws.d_bitsums) cudaFree(ws.d_bitsums);
-            if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
-            ws.d_bitsums = nullptr; ws.h_bitsums = nullptr; ws.cap_partials = 0;
+            ws.d_bitsums = nullptr; ws.cap_partials = 0;
             ZK_CUDA(cudaMalloc(&ws.d_bitsums, need_bits));
-            ZK_CUDA(cudaMallocHost(&ws.h_bitsums, (size_t)G * c * sizeof(xyzz_t)));
             ws.cap_partials = need_bits;
+        }
+        if (ws.cap_hbits < (size_t)G * c) {   // sized by G*c alone: few wide groups and many narrow ones differ
+            if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
+            ws.h_bitsums = nullptr; ws.cap_hbits = 0;
+            ZK_CUDA(cudaMallocHost(&ws.h_bitsums, (size_t)G * c * sizeof(xyzz_t)));
+            ws.cap_hbits = (size_t)G * c;
         }
         if (!ws.d_total) {
             ZK_CUDA(cudaMalloc(&ws.d_total, sizeof(uint32_t)));

@@ -42,7 +42,7 @@ struct MsmBases {
 
 // Growable device scratch of one context/device (sized for the largest call seen so far).
 struct MsmWorkspace {
-    size_t cap_entries = 0, cap_buckets = 0, cap_partials = 0;
+    size_t cap_entries = 0, cap_buckets = 0, cap_partials = 0, cap_hbits = 0;
     int32_t* d_digits = nullptr;      // [nwin][n]
     uint32_t* d_counts = nullptr;     // [G*B]     histogram, then running cursor
     uint32_t* d_offsets = nullptr;    // [G*B + 1] exclusive scan
