@@ -173,6 +173,18 @@ template <class F> static int launch_pass(const NttPassParams& p, size_t batch_y
     return ZK_OK;
 }
 
+// Columns per CTA: as many as the 128 KiB tile allows, but never so many that the grid cannot fill the 148 SMs twice
+// (a 2^16 transform is only 256 columns; 16-column tiles would leave 132 SMs idle).  Keeps >= 4 columns (128 B runs).
+static unsigned pick_log_t(unsigned log_s, size_t ncols, size_t batch) {
+    size_t t = NTT_TILE_ELEMS >> log_s;
+    if (t > ncols) t = ncols;
+    if (t < 1) t = 1;
+    while (t > 4 && ((ncols + t - 1) / t) * batch < 2 * 148) t /= 2;
+    unsigned l = 0;
+    while (((size_t)1 << (l + 1)) <= t) l++;
+    return l;
+}
+
 static unsigned floor_log2(size_t x) {
     unsigned l = 0;
     while ((x >> (l + 1)) != 0) l++;
@@ -220,7 +232,7 @@ int ntt_run(fe* d_data, fe* d_tmp, const fe* d_small, const NttTables& tabs, uns
         NttPassParams p{};
         p.in = d_data; p.out = d_tmp; p.small = d_small; p.lo = tabs.lo; p.hi = tabs.hi;
         p.log_s = log_n1;
-        p.log_t = floor_log2(NTT_TILE_ELEMS >> log_n1 < n2 ? NTT_TILE_ELEMS >> log_n1 : n2);
+        p.log_t = pick_log_t(log_n1, n2, batch);
         p.ncols = (unsigned)n2;
         p.in_row_stride = n2; p.in_col_stride = 1; p.out_row_stride = n2; p.out_col_stride = 1;
         p.batch_stride = n; p.in_len = in_len; p.scale = nullptr; p.col_is_poly = 0;
@@ -231,7 +243,7 @@ int ntt_run(fe* d_data, fe* d_tmp, const fe* d_small, const NttTables& tabs, uns
         NttPassParams q{};
         q.in = d_tmp; q.out = d_data; q.small = d_small; q.lo = nullptr; q.hi = nullptr;
         q.log_s = log_n2;
-        q.log_t = floor_log2(NTT_TILE_ELEMS >> log_n2 < n1 ? NTT_TILE_ELEMS >> log_n2 : n1);
+        q.log_t = pick_log_t(log_n2, n1, batch);
         q.ncols = (unsigned)n1;
         q.in_row_stride = 1; q.in_col_stride = n2; q.out_row_stride = n1; q.out_col_stride = 1;
         q.batch_stride = n; q.in_len = n; q.scale = nullptr; q.col_is_poly = 0;
