@@ -58,9 +58,11 @@ int zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream);
 /* Kernels launched by this context so far (bench.py's gpu_launches). */
 uint64_t zk_ctx_launch_count(const zk_ctx* ctx);
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's roofline line).  After a profiled call
- * zk_ctx_last_stage_ms fills out[0..5] = MSM stages {recode, scan, scatter, accumulate, segreduce, bitsum} of the last
+ * zk_ctx_last_stage_ms fills out[0..5] = MSM stages {recode, plan, scatter, accumulate, finish, bitsum} of the last
  * MSM and out[6] = all kernels of the last NTT call, in milliseconds.  capacity >= 8. */
 int zk_ctx_set_profile(zk_ctx* ctx, int enabled);
+/* Tuning knobs.  "msm_chunk": sorted entries per accumulation task (0 = built-in default). */
+int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value);
 int zk_ctx_last_stage_ms(const zk_ctx* ctx, float* out, size_t capacity);
 
 /* ------------------------------------------------------------------ resident bases

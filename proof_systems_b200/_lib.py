@@ -49,6 +49,7 @@ def lib() -> ctypes.CDLL:
     L.zk_ctx_launch_count.argtypes = [vp]
     L.zk_ctx_launch_count.restype = ctypes.c_uint64
     L.zk_ctx_set_profile.argtypes = [vp, i]
+    L.zk_ctx_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_long]
     L.zk_ctx_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), sz]
     L.zk_bases_upload.argtypes = [vp, i, vp, sz, i, i, ctypes.POINTER(vp)]
     L.zk_bases_free.argtypes = [vp]
@@ -144,10 +145,13 @@ class Context:
     def set_profile(self, enabled: bool):
         check(lib().zk_ctx_set_profile(self._h, int(enabled)))
 
+    def set_option(self, name: str, value: int):
+        check(lib().zk_ctx_set_option(self._h, name.encode(), value))
+
     def last_stage_ms(self) -> dict:
         buf = (ctypes.c_float * 8)()
         check(lib().zk_ctx_last_stage_ms(self._h, buf, 8))
-        names = ["recode", "scan", "scatter", "accumulate", "segreduce", "bitsum", "ntt"]
+        names = ["recode", "plan", "scatter", "accumulate", "finish", "bitsum", "ntt"]
         return {k: float(buf[i]) for i, k in enumerate(names)}
 
     # ------------------------------------------------------------------ MSM

@@ -199,6 +199,8 @@ int zk_ctx_create(int device_id, zk_ctx** out) {
     cudaError_t se = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) { zk_set_error("cudaStreamCreate: %s", cudaGetErrorString(se)); delete ctx; return ZK_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->ws.sm_count = prop.multiProcessorCount;
     *out = ctx;
     return ZK_OK;
 }
@@ -233,6 +235,18 @@ int zk_ctx_set_profile(zk_ctx* ctx, int enabled) {
     ctx->ws.profile = enabled != 0;
     ctx->profile = enabled != 0;
     return ZK_OK;
+}
+
+int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value) {
+    if (!ctx || !name) { zk_set_error("set_option: null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!strcmp(name, "msm_chunk")) {
+        if (value < 0 || value > 4096) { zk_set_error("set_option: msm_chunk %ld outside [0, 4096]", value); return ZK_ERR_INVALID; }
+        ctx->ws.chunk = (uint32_t)value;
+        return ZK_OK;
+    }
+    zk_set_error("set_option: unknown option '%s'", name);
+    return ZK_ERR_INVALID;
 }
 
 int zk_ctx_last_stage_ms(const zk_ctx* ctx, float* out, size_t capacity) {

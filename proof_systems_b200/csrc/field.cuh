@@ -193,7 +193,7 @@ template <class F> ZK_HD fe fe_neg(const fe& a) {
 template <class F> ZK_HD fe fe_dbl(const fe& a) { return fe_add<F>(a, a); }
 
 // One Montgomery reduction row on the carry-save pair (P, S):  t += q*m with q = -t0, making P[0] == 0.
-//   chain alpha: P0 + q (carry is worth S0), q*m1 -> S0:S1, q*m3 -> S2:S3, q*2^30 -> S6:S7
+//   chain alpha: P0 + q (carry is worth S0), q*m1 -> S0:S1, q*m3 -> S2:S3, q*2^30 -> S6:S7 (shifts)
 //   chain beta : q*m2 -> P2:P3, carry rippled to P8
 template <class F> ZK_HD void mont_reduce_row(uint32_t (&P)[9], uint32_t (&S)[9]) {
     // q = -P0 through sub.cc (flag unused): a plain negation gets folded by ptxas into the low half of the next
@@ -206,8 +206,8 @@ template <class F> ZK_HD void mont_reduce_row(uint32_t (&P)[9], uint32_t (&S)[9]
     S[3] = madc_hi_cc(q, F::M3, S[3]);
     S[4] = addc_cc(S[4], 0u);
     S[5] = addc_cc(S[5], 0u);
-    S[6] = madc_lo_cc(q, M7, S[6]);
-    S[7] = madc_hi_cc(q, M7, S[7]);
+    S[6] = addc_cc(S[6], q << 30);   // q * 2^30 with two shifts: keeps the (quarter-rate) IMAD.WIDE pipe for real products
+    S[7] = addc_cc(S[7], q >> 2);
     S[8] = addc(S[8], 0u);
     P[2] = mad_lo_cc(q, F::M2, P[2]);
     P[3] = madc_hi_cc(q, F::M2, P[3]);

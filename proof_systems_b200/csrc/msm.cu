@@ -83,50 +83,79 @@ __global__ void k_recode(const fe* scalars, int scalars_mont, size_t n, unsigned
     }
 }
 
-// Single-CTA exclusive scan of counts[0..nb) -> offsets[0..nb]; clears counts (re-used as scatter cursors).
-__global__ void k_scan(uint32_t* counts, uint32_t* offsets, uint32_t nb, uint32_t* total) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
+// Single-CTA planning pass over the histogram: exclusive scans of the bucket counts (-> offsets of the sorted entry list)
+// and of the per-bucket task counts s_b = ceil(n_b / K) (-> task_off).  Buckets with more than smax tasks ("giant": the
+// all-ones witness columns of kimchi put ~n entries in one bucket) are listed for k_giant_finish.
+// Clears counts (re-used as scatter cursors).
+// 64-bit lanes carry (entry count << 32 | task count): one block scan yields both prefix sums.
+__device__ __forceinline__ uint64_t block_excl_scan_1024(uint64_t v, uint64_t* warp_sums, uint64_t* tile_total) {
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = 0;
+    uint64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (unsigned)d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
     __syncthreads();
-    for (uint32_t base = 0; base < nb; base += 1024) {
-        uint32_t idx = base + tid;
-        uint32_t v = idx < nb ? counts[idx] : 0;
-        if (idx < nb) counts[idx] = 0;
-        uint32_t x = v;
+    if (wid == 0) {
+        uint64_t ws = warp_sums[lane], z = ws;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= (unsigned)d) x += y;
+            uint64_t y = __shfl_up_sync(0xffffffffu, z, d);
+            if (lane >= (unsigned)d) z += y;
         }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t ws = warp_sums[lane];
-            uint32_t z = ws;
+        warp_sums[lane] = z - ws;
+        if (lane == 31) *tile_total = z;
+    }
+    __syncthreads();
+    uint64_t excl = warp_sums[wid] + (x - v);
+    __syncthreads();
+    return excl;
+}
+
+constexpr unsigned PLAN_PER_THREAD = 4;
+__global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offsets, uint32_t* task_off, uint32_t nb, uint32_t K, uint32_t smax,
+                                                 uint32_t* meta /* [0] entries, [1] tasks, [2] giants */, uint32_t* giants) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t tile_total, carry;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) { carry = 0; meta[2] = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024 * PLAN_PER_THREAD) {
+        const uint32_t i0 = base + tid * PLAN_PER_THREAD;
+        uint32_t v[PLAN_PER_THREAD];
+        uint64_t pk[PLAN_PER_THREAD], sum = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, z, d);
-                if (lane >= (unsigned)d) z += y;
+        for (unsigned k = 0; k < PLAN_PER_THREAD; k++) {
+            v[k] = i0 + k < nb ? counts[i0 + k] : 0;
+            if (i0 + k < nb) counts[i0 + k] = 0;
+            pk[k] = ((uint64_t)v[k] << 32) | ((v[k] + K - 1) / K);
+            sum += pk[k];
+        }
+        uint64_t ex = carry + block_excl_scan_1024(sum, warp_sums, &tile_total);
+#pragma unroll
+        for (unsigned k = 0; k < PLAN_PER_THREAD; k++) {
+            if (i0 + k < nb) {
+                offsets[i0 + k] = (uint32_t)(ex >> 32);
+                task_off[i0 + k] = (uint32_t)ex;
+                if ((uint32_t)pk[k] > smax) {
+                    uint32_t gi = atomicAdd(&meta[2], 1u);
+                    if (gi < MSM_MAX_GIANTS) giants[gi] = i0 + k;
+                }
             }
-            warp_sums[lane] = z - ws;  // exclusive
+            ex += pk[k];
         }
         __syncthreads();
-        uint32_t carry = carry_s;
-        uint32_t excl = carry + warp_sums[wid] + (x - v);
-        if (idx < nb) offsets[idx] = excl;
-        __syncthreads();
-        if (tid == 1023) carry_s = excl + v;
+        if (tid == 0) carry += tile_total;
         __syncthreads();
     }
-    if (tid == 0) { offsets[nb] = carry_s; *total = carry_s; }
+    if (tid == 0) { offsets[nb] = (uint32_t)(carry >> 32); task_off[nb] = (uint32_t)carry; meta[0] = (uint32_t)(carry >> 32); meta[1] = (uint32_t)carry; }
 }
 
 // Counting-sort scatter: entry (point index | sign) of every non-zero digit goes to its bucket's range.
 __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned nwin, unsigned groups_per_window, size_t base_off,
-                          size_t table_stride, int use_table, const uint32_t* offsets, uint32_t* cursors, uint32_t* entries,
-                          uint32_t* keys) {
+                          size_t table_stride, int use_table, const uint32_t* offsets, uint32_t* cursors, uint32_t* entries) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n * nwin) return;
     int32_t sd = digits[id];
@@ -139,163 +168,165 @@ __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned 
     uint32_t pos = offsets[key] + atomicAdd(&cursors[key], 1u);
     size_t pidx = (use_table ? (size_t)w * table_stride : 0) + base_off + i;
     entries[pos] = (uint32_t)pidx | (sd < 0 ? 0x80000000u : 0u);
-    keys[pos] = key;
 }
 
-// ---------------------------------------------------------------------------------------------- accumulation, level 0
-// Thread t sums sorted entries [t*K, (t+1)*K).  A run of equal keys that lies strictly inside the chunk is a whole
-// bucket: stored directly.  A run cut by the chunk boundary goes to partial slot 2t (run touching the chunk start) or
-// 2t+1 (run touching the chunk end); a run covering the whole chunk uses slot 2t and an identity in 2t+1 so that equal
-// keys stay contiguous in the partial list.
+// ---------------------------------------------------------------------------------------------- accumulation
+// Task t belongs to the bucket b with task_off[b] <= t < task_off[b+1]; the bucket's n_b sorted entries are cut into
+// s_b = ceil(n_b / K) nearly equal parts, so no task crosses a bucket boundary and every thread sums <= K points with
+// XYZZ mixed additions.  Single-task buckets are written directly, the others leave one partial per task.
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__ points, const uint32_t* __restrict__ entries,
-                                                    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ total_ptr,
-                                                    xyzz_t* buckets, uint32_t* pkeys, xyzz_t* ppts, uint32_t nthreads) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads) return;
-    const uint32_t M = *total_ptr;
-    const uint64_t lo64 = (uint64_t)t * MSM_CHUNK;
-    uint32_t head_key = MSM_KEY_EMPTY, tail_key = MSM_KEY_EMPTY;
-    if (lo64 < M) {
-        const uint32_t lo = (uint32_t)lo64;
-        const uint32_t hi = (M - lo > MSM_CHUNK) ? lo + MSM_CHUNK : M;
-        const uint32_t key_prev = lo > 0 ? keys[lo - 1] : MSM_KEY_EMPTY;
-        const uint32_t key_next = hi < M ? keys[hi] : MSM_KEY_EMPTY;
-        uint32_t cur = keys[lo];
-        bool first = true;
-        xyzz_t acc = xyzz_identity();
-        for (uint32_t i = lo; i < hi; i++) {
-            uint32_t k = keys[i];
-            if (k != cur) {
-                if (first && key_prev == cur) { head_key = cur; store_xyzz(ppts + 2 * (size_t)t, acc); }
-                else store_xyzz(buckets + cur, acc);
-                first = false;
-                cur = k;
-                acc = xyzz_identity();
-            }
-            uint32_t e = entries[i];
-            affine_t p = load_affine_nc(points + (e & 0x7fffffffu));
-            if (e >> 31) p.y = fe_neg<F>(p.y);
-            acc = xyzz_madd<F>(acc, p);
-        }
-        const bool cont_prev = first && key_prev == cur, cont_next = key_next == cur;
-        if (!cont_prev && !cont_next) store_xyzz(buckets + cur, acc);
-        else if (first) {
-            head_key = cur;
-            store_xyzz(ppts + 2 * (size_t)t, acc);
-            if (cont_next) { tail_key = cur; store_xyzz(ppts + 2 * (size_t)t + 1, xyzz_identity()); }
-        } else {
-            tail_key = cur;
-            store_xyzz(ppts + 2 * (size_t)t + 1, acc);
-        }
+                                                    const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
+                                                    uint32_t K, const uint32_t* __restrict__ meta, xyzz_t* buckets, xyzz_t* partials) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= meta[1]) return;
+    // upper_bound(task_off[0..nb], t) - 1
+    uint32_t lo = 0, hi = nb;  // invariant: task_off[lo] <= t < task_off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid;
     }
-    pkeys[2 * (size_t)t] = head_key;
-    pkeys[2 * (size_t)t + 1] = tail_key;
+    const uint32_t b = lo;
+    const uint32_t e0 = __ldg(offsets + b), nbk = __ldg(offsets + b + 1) - e0;
+    const uint32_t sb = (nbk + K - 1) / K, sub = t - __ldg(task_off + b);
+    const uint32_t base = nbk / sb, rem = nbk - base * sb;
+    uint32_t i = e0 + sub * base + min(sub, rem);
+    const uint32_t end = i + base + (sub < rem ? 1u : 0u);
+    xyzz_t acc = xyzz_identity();
+    // software pipeline: the gather of point i+1 is in flight while point i is added
+    uint32_t e = __ldg(entries + i);
+    affine_t p = load_affine_nc(points + (e & 0x7fffffffu));
+    for (; i < end; i++) {
+        affine_t q = p;
+        const uint32_t sign = e >> 31;
+        if (i + 1 < end) {
+            e = __ldg(entries + i + 1);
+            p = load_affine_nc(points + (e & 0x7fffffffu));
+        }
+        if (sign) q.y = fe_neg<F>(q.y);
+        acc = xyzz_madd<F>(acc, q);
+    }
+    store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
 }
 
-// ---------------------------------------------------------------------------------------------- partial-list levels
-// One warp per 32 consecutive partials: segmented inclusive scan by key with warp shuffles; the last lane of a run holds
-// the run's sum.  Runs that do not continue into the neighbouring warps are whole buckets (stored); the others go to
-// the next, 16x shorter partial list.
+// Buckets with 2 <= s_b <= smax tasks: a group of G = 2^log_g lanes sums the bucket's partials (strided), then a
+// shuffle tree of log_g levels.  Thread-per-bucket (G = 1) when buckets hold only a few partials.
 template <class F>
-__global__ void __launch_bounds__(128) k_segreduce(const uint32_t* __restrict__ pkeys_in, const xyzz_t* __restrict__ ppts_in, uint32_t n_in,
-                                                   xyzz_t* buckets, uint32_t* pkeys_out, xyzz_t* ppts_out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31, wg = i >> 5;
-    if (wg * 32 >= n_in) return;  // whole warp out of range
-    uint32_t key = i < n_in ? pkeys_in[i] : MSM_KEY_EMPTY;
-    xyzz_t pt = xyzz_identity();
-    if (key != MSM_KEY_EMPTY) pt = load_xyzz(ppts_in + i);
+__global__ void __launch_bounds__(128) k_bucket_finish(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
+                                                       uint32_t K, uint32_t smax, unsigned log_g, const uint32_t* __restrict__ meta,
+                                                       xyzz_t* buckets, const xyzz_t* __restrict__ partials) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t G = 1u << log_g, b = gt >> log_g, gl = gt & (G - 1);
+    uint32_t sb = 0, t0 = 0;
+    if (b < nb) {
+        const uint32_t nbk = __ldg(offsets + b + 1) - __ldg(offsets + b);
+        sb = (nbk + K - 1) / K;
+        t0 = __ldg(task_off + b);
+        // giants are left to k_giant_finish — unless their list overflowed, then they are summed here (slow, correct)
+        if (sb > smax && meta[2] <= MSM_MAX_GIANTS) sb = 0;
+        if (sb < 2) sb = 0;
+    }
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t j = gl; j < sb; j += G) acc = xyzz_add<F>(acc, load_xyzz(partials + t0 + j));
 #pragma unroll 1
-    for (unsigned d = 1; d < 32; d <<= 1) {
-        uint32_t okey = __shfl_up_sync(0xffffffffu, key, d);
-        xyzz_t opt = shfl_up_xyzz(pt, d);
-        if (lane >= d && okey == key && key != MSM_KEY_EMPTY) pt = xyzz_add<F>(opt, pt);
+    for (unsigned d = G >> 1; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, d);
+        if (gl < d) acc = xyzz_add<F>(acc, o);
     }
-    const uint32_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-    const uint32_t next_key = __shfl_down_sync(0xffffffffu, key, 1);
-    const bool is_head = lane == 0 || prev_key != key;
-    const uint32_t heads = __ballot_sync(0xffffffffu, is_head);
-    const bool run_end = lane == 31 || next_key != key;
-    if (lane == 0) { pkeys_out[2 * (size_t)wg] = MSM_KEY_EMPTY; pkeys_out[2 * (size_t)wg + 1] = MSM_KEY_EMPTY; }
-    __syncwarp();
-    if (run_end && key != MSM_KEY_EMPTY) {
-        const uint32_t below = heads & (0xffffffffu >> (31 - lane));
-        const uint32_t start = 31 - __clz(below);
-        const uint32_t w0 = wg * 32;
-        const bool cont_prev = start == 0 && w0 > 0 && pkeys_in[w0 - 1] == key;
-        const bool cont_next = lane == 31 && w0 + 32 < n_in && pkeys_in[w0 + 32] == key;
-        if (!cont_prev && !cont_next) store_xyzz(buckets + key, pt);
-        else if (start == 0) {
-            pkeys_out[2 * (size_t)wg] = key;
-            store_xyzz(ppts_out + 2 * (size_t)wg, pt);
-            if (cont_next) { pkeys_out[2 * (size_t)wg + 1] = key; store_xyzz(ppts_out + 2 * (size_t)wg + 1, xyzz_identity()); }
-        } else {
-            pkeys_out[2 * (size_t)wg + 1] = key;
-            store_xyzz(ppts_out + 2 * (size_t)wg + 1, pt);
-        }
-    }
+    if (gl == 0 && sb) store_xyzz(buckets + b, acc);
 }
 
 // ---------------------------------------------------------------------------------------------- bucket reduction
 // sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of (b+1) set.
 // grid (blocks_per_bit, c, G); every CTA tree-sums its slice of one group's buckets for one bit.
-constexpr unsigned BITSUM_THREADS = 128;
-template <class F> __device__ __forceinline__ xyzz_t block_sum(xyzz_t acc, xyzz_t* sm) {
-    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll 1
-    for (unsigned d = 16; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, d);
-        if (lane < d) acc = xyzz_add<F>(acc, o);
-    }
-    if (lane == 0) sm[wid] = acc;
+// Block-wide point sum through shared memory with re-compaction: after every level the live partials are the first
+// `stride` threads, so whole warps retire early and only the last five levels run with a partly filled warp (a shuffle
+// tree would keep every warp busy for five full additions).  blockDim.x must be a power of two <= TREE_THREADS.
+constexpr unsigned TREE_THREADS = 256;
+template <class F> __device__ __forceinline__ xyzz_t block_tree_sum(xyzz_t acc, xyzz_t* sm) {
+    const unsigned tid = threadIdx.x;
+    store_xyzz(sm + tid, acc);
     __syncthreads();
-    if (wid == 0) {
-        const unsigned nw = blockDim.x >> 5;
-        acc = lane < nw ? sm[lane] : xyzz_identity();
 #pragma unroll 1
-        for (unsigned d = 16; d >= 1; d >>= 1) {
-            xyzz_t o = shfl_down_xyzz(acc, d);
-            if (lane < d && d < 2 * nw) acc = xyzz_add<F>(acc, o);
+    for (unsigned stride = blockDim.x >> 1; stride >= 1; stride >>= 1) {
+        if (tid < stride) {
+            acc = xyzz_add<F>(acc, load_xyzz(sm + tid + stride));
+            store_xyzz(sm + tid, acc);
         }
+        __syncthreads();
     }
     return acc;  // valid in thread 0
 }
 
+// One CTA per giant bucket: strided serial sums of its partial list, then the block tree.
 template <class F>
-__global__ void __launch_bounds__(BITSUM_THREADS) k_bitsum(const xyzz_t* __restrict__ buckets, uint32_t B, xyzz_t* partial) {
-    __shared__ xyzz_t sm[BITSUM_THREADS / 32];
-    const unsigned t = blockIdx.y, g = blockIdx.z, nblk = gridDim.x;
-    const uint32_t per = (B + nblk - 1) / nblk;
-    const uint32_t b0 = blockIdx.x * per, b1 = min(B, b0 + per);
+__global__ void __launch_bounds__(TREE_THREADS) k_giant_finish(const uint32_t* __restrict__ giants, const uint32_t* __restrict__ meta,
+                                                               const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t K,
+                                                               xyzz_t* buckets, const xyzz_t* __restrict__ partials) {
+    extern __shared__ xyzz_t sm_tree[];
+    const uint32_t ng = meta[2];
+    if (ng > MSM_MAX_GIANTS || blockIdx.x >= ng) return;  // overflow: k_bucket_finish took them
+    const uint32_t b = giants[blockIdx.x];
+    const uint32_t nbk = offsets[b + 1] - offsets[b], sb = (nbk + K - 1) / K, t0 = task_off[b];
     xyzz_t acc = xyzz_identity();
-    for (uint32_t b = b0 + threadIdx.x; b < b1; b += blockDim.x)
-        if (((b + 1) >> t) & 1u) acc = xyzz_add<F>(acc, load_xyzz(buckets + (size_t)g * B + b));
-    acc = block_sum<F>(acc, sm);
-    if (threadIdx.x == 0) store_xyzz(partial + ((size_t)g * gridDim.y + t) * nblk + blockIdx.x, acc);
+    for (uint32_t j = threadIdx.x; j < sb; j += blockDim.x) acc = xyzz_add<F>(acc, load_xyzz(partials + t0 + j));
+    acc = block_tree_sum<F>(acc, sm_tree);
+    if (threadIdx.x == 0) store_xyzz(buckets + b, acc);
 }
 
-// second stage: one warp per (group, bit) sums the <= 32 CTA partials
-template <class F> __global__ void k_bitsum_final(const xyzz_t* __restrict__ partial, unsigned nblk, xyzz_t* out) {
-    const unsigned lane = threadIdx.x;
-    xyzz_t acc = lane < nblk ? load_xyzz(partial + (size_t)blockIdx.x * nblk + lane) : xyzz_identity();
-#pragma unroll 1
-    for (unsigned d = 16; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, d);
-        if (lane < d) acc = xyzz_add<F>(acc, o);
+// sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of i = b+1 set, i in [1, B], B = 2^(c-1).
+// For t < c-1 exactly B/2 indices qualify; the j-th is i = (j >> t) << (t+1) | 1 << t | (j & (2^t - 1)).  Slice c-1 is the
+// single bucket i = B.  grid (blocks_per_bit, c-1, G): every CTA sums a contiguous range of j (coalesced runs of 2^t
+// buckets), a few per thread, then the block tree.
+template <class F>
+__global__ void __launch_bounds__(TREE_THREADS, 2) k_bitsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned c, xyzz_t* partial) {
+    extern __shared__ xyzz_t sm_tree[];
+    const unsigned t = blockIdx.y, g = blockIdx.z, nblk = gridDim.x;
+    const uint32_t half = B >> 1, per = (half + nblk - 1) / nblk;
+    const uint32_t j0 = blockIdx.x * per, j1 = min(half, j0 + per);
+    const xyzz_t* bk = buckets + (size_t)g * B;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+        uint32_t i = ((j >> t) << (t + 1)) | (1u << t) | (j & ((1u << t) - 1));
+        acc = xyzz_add<F>(acc, load_xyzz(bk + (i - 1)));
     }
-    if (lane == 0) store_xyzz(out + blockIdx.x, acc);
+    acc = block_tree_sum<F>(acc, sm_tree);
+    if (threadIdx.x == 0) store_xyzz(partial + ((size_t)g * c + t) * nblk + blockIdx.x, acc);
+}
+
+// second stage: one small CTA per (group, bit) sums the CTA partials; bit c-1 is copied from its bucket.
+template <class F>
+__global__ void __launch_bounds__(64) k_bitsum_final(const xyzz_t* __restrict__ partial, const xyzz_t* __restrict__ buckets, uint32_t B, unsigned c,
+                                                     unsigned nblk, xyzz_t* out) {
+    extern __shared__ xyzz_t sm_tree[];
+    const unsigned g = blockIdx.x / c, t = blockIdx.x % c;
+    xyzz_t acc = xyzz_identity();
+    if (t == c - 1) {
+        if (threadIdx.x == 0) acc = load_xyzz(buckets + (size_t)g * B + (B - 1));
+    } else {
+        for (unsigned j = threadIdx.x; j < nblk; j += blockDim.x) acc = xyzz_add<F>(acc, load_xyzz(partial + (size_t)blockIdx.x * nblk + j));
+    }
+    acc = block_tree_sum<F>(acc, sm_tree);
+    if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, acc);
 }
 
 // ---------------------------------------------------------------------------------------------- workspace
+// ---------------------------------------------------------------------------------------------- workspace
+static void free_dev(void* p) { if (p) cudaFree(p); }
+
 void msm_workspace_free(MsmWorkspace& ws) {
-    void* ptrs[] = {ws.d_digits, ws.d_counts, ws.d_offsets, ws.d_entries, ws.d_keys, ws.d_buckets,
-                    ws.d_pkeys[0], ws.d_pkeys[1], ws.d_ppts[0], ws.d_ppts[1], ws.d_bitsums, ws.d_total};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    free_dev(ws.d_digits); free_dev(ws.d_entries); free_dev(ws.d_partials);
+    free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_buckets);
+    free_dev(ws.d_bitsums); free_dev(ws.d_meta); free_dev(ws.d_giants);
     if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
-    if (ws.h_total) cudaFreeHost(ws.h_total);
     for (auto& e : ws.ev) if (e) cudaEventDestroy(e);
     ws = MsmWorkspace();
+}
+
+static unsigned pow2_ceil_log(uint64_t x) {
+    unsigned l = 0;
+    while (((uint64_t)1 << l) < x) l++;
+    return l;
 }
 
 template <class F, class FS>
@@ -314,49 +345,62 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     const size_t NB = (size_t)G * B;
     const size_t Mmax = n * nwin;
     if (Mmax >= 0x7fffffffull || b.n * (size_t)std::max(1u, b.nwin) >= 0x7fffffffull) { zk_set_error("msm: %zu x %u entries exceed the 31-bit index space", n, nwin); return ZK_ERR_INVALID; }
-    const uint32_t T0 = (uint32_t)((Mmax + MSM_CHUNK - 1) / MSM_CHUNK);
-    const unsigned nblk = (unsigned)std::min<size_t>(32, std::max<size_t>(1, B / (BITSUM_THREADS * 2)));
+    // Entries per accumulation task: the accumulate kernel keeps `capacity` threads resident (4 CTAs of 128 per SM at
+    // <= 128 registers); K is chosen so that the tasks fill a whole number of waves (a 1.02-wave grid costs two waves).
+    const size_t capacity = (size_t)ws.sm_count * 512;
+    uint32_t K = ws.chunk;
+    if (K == 0) {
+        const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
+        size_t waves = (Mmax + 24 * capacity - 1) / (24 * capacity);
+        if (waves == 0) waves = 1;
+        K = (uint32_t)((Mmax + waves * capacity - slack - 1) / (waves * capacity - slack));
+        if (K < 4) K = 4;
+    }
+    const size_t NTmax = Mmax / K + NB + 1;           // sum_b ceil(n_b / K) <= M / K + (number of non-empty buckets)
+    // lanes per bucket in the finish pass: ~a quarter of the expected partials per bucket
+    const uint64_t s_avg = Mmax / ((uint64_t)K * NB) + 1;
+    unsigned log_g = pow2_ceil_log((s_avg + 3) / 4);
+    if (log_g > 5) log_g = 5;
+    const uint32_t smax = 32u << log_g;               // more partials than this: the bucket is "giant"
+    // bit-sliced bucket sums: (c-1) slices of B/2 elements; elements per thread chosen so that all CTAs are resident at once
+    const unsigned bs_threads = (unsigned)std::min<uint32_t>(TREE_THREADS, std::max<uint32_t>(32, B / 2));
+    size_t per_thread = ((size_t)(c - 1) * (B / 2) * G + (size_t)ws.sm_count * 512 - 1) / ((size_t)ws.sm_count * 512);
+    if (per_thread < 2) per_thread = 2;
+    unsigned nblk = 1;
+    while (nblk < 64 && (size_t)nblk * 2 * bs_threads * per_thread <= B / 2) nblk *= 2;
 
-    // scratch (grown on demand, reused across calls)
     static_assert(sizeof(xyzz_t) == 128 && sizeof(affine_t) == 64 && sizeof(fe) == 32, "layout");
-    // buffers are grouped by what sizes them: the entry list (n * nwin), the bucket array (G * B), the bit sums (G * c)
+    // scratch, grouped by what sizes it: the entry list (n * nwin), the bucket array (G * B), the bit sums (G * c)
     {
-        size_t need_digits = Mmax * sizeof(int32_t), need_counts = NB * sizeof(uint32_t), need_offsets = (NB + 1) * sizeof(uint32_t);
-        size_t need_entries = Mmax * sizeof(uint32_t), need_buckets = NB * sizeof(xyzz_t);
-        size_t need_pk = 2 * (size_t)T0 * sizeof(uint32_t), need_pp = 2 * (size_t)T0 * sizeof(xyzz_t);
-        size_t need_bits = (size_t)G * c * nblk * sizeof(xyzz_t) + (size_t)G * c * sizeof(xyzz_t);
+        const size_t need_entries = Mmax * sizeof(uint32_t), need_partials = NTmax * sizeof(xyzz_t);
         if (ws.cap_entries < need_entries) {
-            if (ws.d_digits) cudaFree(ws.d_digits);
-            if (ws.d_entries) cudaFree(ws.d_entries);
-            if (ws.d_keys) cudaFree(ws.d_keys);
-            for (int k = 0; k < 2; k++) { if (ws.d_pkeys[k]) cudaFree(ws.d_pkeys[k]); if (ws.d_ppts[k]) cudaFree(ws.d_ppts[k]); }
-            ws.d_digits = nullptr; ws.d_entries = ws.d_keys = nullptr; ws.d_pkeys[0] = ws.d_pkeys[1] = nullptr; ws.d_ppts[0] = ws.d_ppts[1] = nullptr;
-            ws.cap_entries = 0;
-            ZK_CUDA(cudaMalloc(&ws.d_digits, need_digits));
+            free_dev(ws.d_digits); free_dev(ws.d_entries);
+            ws.d_digits = nullptr; ws.d_entries = nullptr; ws.cap_entries = 0;
+            ZK_CUDA(cudaMalloc(&ws.d_digits, Mmax * sizeof(int32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_entries, need_entries));
-            ZK_CUDA(cudaMalloc(&ws.d_keys, need_entries));
-            ZK_CUDA(cudaMalloc(&ws.d_pkeys[0], need_pk));
-            ZK_CUDA(cudaMalloc(&ws.d_ppts[0], need_pp));
-            size_t n1 = 2 * (((size_t)2 * T0 + 31) / 32);
-            ZK_CUDA(cudaMalloc(&ws.d_pkeys[1], std::max<size_t>(n1, 2) * sizeof(uint32_t)));
-            ZK_CUDA(cudaMalloc(&ws.d_ppts[1], std::max<size_t>(n1, 2) * sizeof(xyzz_t)));
             ws.cap_entries = need_entries;
         }
-        if (ws.cap_buckets < need_buckets) {
-            if (ws.d_counts) cudaFree(ws.d_counts);
-            if (ws.d_offsets) cudaFree(ws.d_offsets);
-            if (ws.d_buckets) cudaFree(ws.d_buckets);
-            ws.d_counts = ws.d_offsets = nullptr; ws.d_buckets = nullptr; ws.cap_buckets = 0;
-            ZK_CUDA(cudaMalloc(&ws.d_counts, need_counts));
-            ZK_CUDA(cudaMalloc(&ws.d_offsets, need_offsets));
-            ZK_CUDA(cudaMalloc(&ws.d_buckets, need_buckets));
-            ws.cap_buckets = need_buckets;
+        if (ws.cap_partials < need_partials) {
+            free_dev(ws.d_partials);
+            ws.d_partials = nullptr; ws.cap_partials = 0;
+            ZK_CUDA(cudaMalloc(&ws.d_partials, need_partials));
+            ws.cap_partials = need_partials;
         }
-        if (ws.cap_partials < need_bits) {
-            if (ws.d_bitsums) cudaFree(ws.d_bitsums);
-            ws.d_bitsums = nullptr; ws.cap_partials = 0;
-            ZK_CUDA(cudaMalloc(&ws.d_bitsums, need_bits));
-            ws.cap_partials = need_bits;
+        if (ws.cap_buckets < NB) {
+            free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_buckets);
+            ws.d_counts = ws.d_offsets = ws.d_task_off = nullptr; ws.d_buckets = nullptr; ws.cap_buckets = 0;
+            ZK_CUDA(cudaMalloc(&ws.d_counts, NB * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_offsets, (NB + 1) * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_task_off, (NB + 1) * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_buckets, NB * sizeof(xyzz_t)));
+            ws.cap_buckets = NB;
+        }
+        const size_t need_bits = (size_t)G * c * (nblk + 1);
+        if (ws.cap_bits < need_bits) {
+            free_dev(ws.d_bitsums);
+            ws.d_bitsums = nullptr; ws.cap_bits = 0;
+            ZK_CUDA(cudaMalloc(&ws.d_bitsums, need_bits * sizeof(xyzz_t)));
+            ws.cap_bits = need_bits;
         }
         if (ws.cap_hbits < (size_t)G * c) {   // sized by G*c alone: few wide groups and many narrow ones differ
             if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
@@ -364,9 +408,9 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
             ZK_CUDA(cudaMallocHost(&ws.h_bitsums, (size_t)G * c * sizeof(xyzz_t)));
             ws.cap_hbits = (size_t)G * c;
         }
-        if (!ws.d_total) {
-            ZK_CUDA(cudaMalloc(&ws.d_total, sizeof(uint32_t)));
-            ZK_CUDA(cudaMallocHost(&ws.h_total, sizeof(uint32_t)));
+        if (!ws.d_meta) {
+            ZK_CUDA(cudaMalloc(&ws.d_meta, 4 * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_giants, MSM_MAX_GIANTS * sizeof(uint32_t)));
         }
     }
     unsigned nl = 0;
@@ -374,41 +418,35 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
         for (int k = 0; k <= MSM_ST_COUNT; k++) ZK_CUDA(cudaEventCreate(&ws.ev[k]));
 #define STAGE_MARK(k) do { if (ws.profile) ZK_CUDA(cudaEventRecord(ws.ev[k], st)); } while (0)
 
-    // 1. digits + histogram
     ZK_CUDA(cudaMemsetAsync(ws.d_counts, 0, NB * sizeof(uint32_t), st));
     ZK_CUDA(cudaMemsetAsync(ws.d_buckets, 0, NB * sizeof(xyzz_t), st));  // all-zero XYZZ == identity
     STAGE_MARK(0);
+    // 1. digits + histogram
     k_recode<FS><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_scalars_in, scalars_mont ? 1 : 0, n, c, nwin, use_table ? 0 : 1, ws.d_digits, ws.d_counts);
     STAGE_MARK(1);
-    // 2. bucket offsets
-    k_scan<<<1, 1024, 0, st>>>(ws.d_counts, ws.d_offsets, (uint32_t)NB, ws.d_total);
+    // 2. plan: bucket offsets, task offsets, giant list
+    k_plan<<<1, 1024, 0, st>>>(ws.d_counts, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, ws.d_giants);
     STAGE_MARK(2);
     // 3. scatter (counting sort by bucket)
     k_scatter<<<(unsigned)((Mmax + 255) / 256), 256, 0, st>>>(ws.d_digits, n, c, nwin, use_table ? 0 : 1, off, b.n, use_table ? 1 : 0,
-                                                            ws.d_offsets, ws.d_counts, ws.d_entries, ws.d_keys);
+                                                            ws.d_offsets, ws.d_counts, ws.d_entries);
     STAGE_MARK(3);
-    // 4. balanced accumulation over the sorted list
-    k_accumulate<F><<<(T0 + 127) / 128, 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_keys, ws.d_total, ws.d_buckets, ws.d_pkeys[0], ws.d_ppts[0], T0);
-    nl += 4;
+    // 4. accumulation: one task per <= K sorted entries of one bucket
+    k_accumulate<F><<<(unsigned)((NTmax + 127) / 128), 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, ws.d_meta,
+                                                                   ws.d_buckets, ws.d_partials);
     STAGE_MARK(4);
-    // 5. partial-list levels
-    uint32_t n_in = 2 * T0;
-    int cur = 0;
-    for (;;) {
-        uint32_t warps = (n_in + 31) / 32;
-        k_segreduce<F><<<(warps * 32 + 127) / 128, 128, 0, st>>>(ws.d_pkeys[cur], ws.d_ppts[cur], n_in, ws.d_buckets, ws.d_pkeys[cur ^ 1], ws.d_ppts[cur ^ 1]);
-        nl++;
-        if (warps == 1) break;
-        n_in = 2 * warps;
-        cur ^= 1;
-    }
+    // 5. per-bucket sums of the task partials (+ giants)
+    k_bucket_finish<F><<<(unsigned)(((NB << log_g) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
+                                                                              ws.d_buckets, ws.d_partials);
+    k_giant_finish<F><<<MSM_MAX_GIANTS, TREE_THREADS, TREE_THREADS * sizeof(xyzz_t), st>>>(ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials);
     STAGE_MARK(5);
     // 6. bit-sliced bucket sums
     xyzz_t* d_partial = ws.d_bitsums;
     xyzz_t* d_T = ws.d_bitsums + (size_t)G * c * nblk;
-    k_bitsum<F><<<dim3(nblk, c, G), BITSUM_THREADS, 0, st>>>(ws.d_buckets, B, d_partial);
-    k_bitsum_final<F><<<G * c, 32, 0, st>>>(d_partial, nblk, d_T);
-    nl += 2;
+    if (c > 1 && B >= 2)
+        k_bitsum<F><<<dim3(nblk, c - 1, G), bs_threads, bs_threads * sizeof(xyzz_t), st>>>(ws.d_buckets, B, c, d_partial);
+    k_bitsum_final<F><<<G * c, 64, 64 * sizeof(xyzz_t), st>>>(d_partial, ws.d_buckets, B, c, nblk, d_T);
+    nl += 8;
     STAGE_MARK(6);
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaMemcpyAsync(ws.h_bitsums, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));

@@ -13,11 +13,10 @@
 //     window and the host combines the windows.
 //   * scalars are recoded to signed base-2^c digits in (-2^(c-1), 2^(c-1)]; (digit != 0) entries are counting-sorted by
 //     bucket (histogram -> scan -> scatter, all on device);
-//   * accumulation is a balanced segmented reduction over the SORTED entry list: every thread sums a fixed-size chunk
-//     of consecutive entries with XYZZ mixed additions, whole runs go straight to their bucket, runs cut by a chunk
-//     boundary go to a partial list that is reduced with warp-shuffle segmented scans, level by level.  Work per
-//     thread is identical whatever the scalar distribution (all points in one bucket — the kimchi witness columns,
-//     SURVEY.md §3.1 — costs the same as uniform scalars), and no atomics touch curve points;
+//   * accumulation is task based: the histogram is known before any point is touched, so every bucket's sorted entries
+//     are cut into ceil(n_b / K) nearly equal tasks; a thread sums one task (<= K XYZZ mixed additions), a small lane
+//     group per bucket sums the task partials with a shuffle tree, and the rare giant bucket (all points in one
+//     bucket — the kimchi witness columns) gets a whole CTA.  No atomics touch curve points;
 //   * bucket reduction sum_b (b+1) B_b is evaluated bit-sliced: T_t = sum of the buckets whose (b+1) has bit t set —
 //     c masked tree sums, fully parallel — and the host finishes with c doublings.
 #pragma once
@@ -28,8 +27,7 @@
 namespace zkb {
 
 constexpr unsigned MSM_MAX_WINDOW_BITS = 16;
-constexpr unsigned MSM_CHUNK = 16;           // sorted entries per thread in the accumulation kernel
-constexpr uint32_t MSM_KEY_EMPTY = 0xffffffffu;
+constexpr uint32_t MSM_MAX_GIANTS = 64;       // buckets with > smax tasks get a CTA each (k_giant_finish)
 
 // A resident set of bases on one device.
 struct MsmBases {
@@ -42,19 +40,20 @@ struct MsmBases {
 
 // Growable device scratch of one context/device (sized for the largest call seen so far).
 struct MsmWorkspace {
-    size_t cap_entries = 0, cap_buckets = 0, cap_partials = 0, cap_hbits = 0;
+    size_t cap_entries = 0, cap_partials = 0, cap_buckets = 0, cap_bits = 0, cap_hbits = 0;
     int32_t* d_digits = nullptr;      // [nwin][n]
-    uint32_t* d_counts = nullptr;     // [G*B]     histogram, then running cursor
-    uint32_t* d_offsets = nullptr;    // [G*B + 1] exclusive scan
     uint32_t* d_entries = nullptr;    // [M]  point index | sign << 31, sorted by bucket
-    uint32_t* d_keys = nullptr;       // [M]  bucket id of every sorted entry
+    xyzz_t* d_partials = nullptr;     // [tasks] one partial sum per accumulation task
+    uint32_t* d_counts = nullptr;     // [G*B]     histogram, then scatter cursors
+    uint32_t* d_offsets = nullptr;    // [G*B + 1] exclusive scan of the counts
+    uint32_t* d_task_off = nullptr;   // [G*B + 1] exclusive scan of ceil(count / K)
     xyzz_t* d_buckets = nullptr;      // [G*B]
-    uint32_t* d_pkeys[2] = {nullptr, nullptr};  // partial lists (ping-pong)
-    xyzz_t* d_ppts[2] = {nullptr, nullptr};
-    xyzz_t* d_bitsums = nullptr;      // [G][c][BITSUM_BLOCKS] then [G][c]
+    xyzz_t* d_bitsums = nullptr;      // [G][c][blocks] then [G][c]
     xyzz_t* h_bitsums = nullptr;      // pinned host copy of [G][c]
-    uint32_t* d_total = nullptr;      // [1] number of sorted entries
-    uint32_t* h_total = nullptr;      // pinned
+    uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets
+    uint32_t* d_giants = nullptr;     // [MSM_MAX_GIANTS] bucket ids
+    uint32_t chunk = 0;               // K override (0: chosen per call so that the tasks fill whole waves)
+    int sm_count = 148;               // SMs of the device (set by the context)
     bool profile = false;             // record an event after every stage
     cudaEvent_t ev[8] = {};           // MSM_ST_COUNT + 1 stage boundaries
     float stage_ms[8] = {};           // duration of each stage in the last profiled call
@@ -69,7 +68,7 @@ template <class F> int msm_bases_create(MsmBases& b, const affine_t* pts, bool p
 void msm_bases_free(MsmBases& b);
 
 // Optional per-stage device timing (CUDA events on the launching stream), filled when MsmWorkspace::profile is set.
-enum MsmStage { MSM_ST_RECODE = 0, MSM_ST_SCAN, MSM_ST_SCATTER, MSM_ST_ACCUMULATE, MSM_ST_SEGREDUCE, MSM_ST_BITSUM, MSM_ST_COUNT };
+enum MsmStage { MSM_ST_RECODE = 0, MSM_ST_PLAN, MSM_ST_SCATTER, MSM_ST_ACCUMULATE, MSM_ST_FINISH, MSM_ST_BITSUM, MSM_ST_COUNT };
 
 // What msm_run leaves in ws.h_bitsums: groups x c XYZZ points T[g][t]; the MSM is sum_g 2^(c g) sum_t 2^t T[g][t].
 struct MsmResultShape {

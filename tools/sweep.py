@@ -40,12 +40,14 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "msm"):
     z = np.load(os.path.join(ROOT, "tests", "golden", "pallas_srs.npz"))
     g = orc.decompress(orc.PALLAS, z["g_cmp"].tobytes())
-    for log_n, windows in ((11, (0, 8, 10)), (16, (0, 11, 12, 13, 14, 15, 16))):
+    chunks = [int(x) for x in os.environ.get("CHUNKS", "16").split(",")]
+    for log_n, windows in ((11, (0, 8, 10)), (16, (0, 12, 13, 14, 15, 16))):
         n = 1 << log_n
         sc = orc.random_scalars(orc.FQ, n, seed=1)
         d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
         want = orc.msm(orc.PALLAS, g[:n], sc)
-        for wb in windows:
+        for wb, chunk in [(w, k) for w in windows for k in chunks]:
+            ctx.set_option("msm_chunk", chunk)
             t0 = time.time()
             bases = ctx.upload_bases(zk.PALLAS, g[:n], window_bits=wb)
             up = time.time() - t0
@@ -56,7 +58,7 @@ if which in ("all", "msm"):
             ctx.msm_dev(bases, d_sc.data_ptr(), n)
             st = ctx.last_stage_ms()
             ctx.set_profile(False)
-            row = {"log_n": log_n, "window_bits": wb, "ms": ms, "points_per_s": n / ms * 1e3, "ok": ok, "upload_s": up,
+            row = {"log_n": log_n, "window_bits": wb, "chunk": chunk, "ms": ms, "points_per_s": n / ms * 1e3, "ok": ok, "upload_s": up,
                    "stages": {k: round(v, 4) for k, v in st.items() if k != "ntt"}}
             out["msm"].append(row)
             print(json.dumps(row), flush=True)
