@@ -1,5 +1,6 @@
 // msm.cu — kernels and pipeline of the Pallas/Vesta MSM (see msm.cuh for semantics and reference call sites).
 #include "msm.cuh"
+#include "quad.cuh"
 
 #include <algorithm>
 
@@ -8,10 +9,11 @@ namespace zkb {
 unsigned msm_num_windows(unsigned c) { return (256 + c - 1) / c; }  // top signed digit cannot carry out (scalars < 2^254 + 2^127)
 
 int msm_default_window(size_t n, bool precomputed) {
-    // accumulation costs nwin(c) * n mixed additions, the bit-sliced bucket reduction ~ c * 2^(c-2) full additions
+    // accumulation costs ceil(256/c) * n mixed additions; the bucket side grows with 2^(c-1) (one bucket set with a
+    // table, one per window without).  Measured on B200 (tools/sweep.py): 2^16 points -> c = 15 with a table, 12 without.
     unsigned l = 0;
     while (((size_t)1 << (l + 1)) <= n) l++;
-    int c = (int)l - (precomputed ? 3 : 4);
+    int c = (int)l - (precomputed ? 1 : 4);
     if (c < 4) c = 4;
     if (c > (int)MSM_MAX_WINDOW_BITS) c = MSM_MAX_WINDOW_BITS;
     return c;
@@ -209,14 +211,14 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
     store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
 }
 
-// Buckets with 2 <= s_b <= smax tasks: a group of G = 2^log_g lanes sums the bucket's partials (strided), then a
-// shuffle tree of log_g levels.  Thread-per-bucket (G = 1) when buckets hold only a few partials.
+// Buckets with 2 <= s_b <= smax tasks: a group of G = 2^log_g QUADS (quad.cuh) sums the bucket's partials — strided serial
+// part, then a shuffle tree over the quads of the group.  One quad per bucket when buckets hold only a few partials.
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_finish(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
                                                        uint32_t K, uint32_t smax, unsigned log_g, const uint32_t* __restrict__ meta,
                                                        xyzz_t* buckets, const xyzz_t* __restrict__ partials) {
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t G = 1u << log_g, b = gt >> log_g, gl = gt & (G - 1);
+    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // global quad
+    const uint32_t G = 1u << log_g, b = gq >> log_g, gl = gq & (G - 1);
     uint32_t sb = 0, t0 = 0;
     if (b < nb) {
         const uint32_t nbk = __ldg(offsets + b + 1) - __ldg(offsets + b);
@@ -226,39 +228,31 @@ __global__ void __launch_bounds__(128) k_bucket_finish(const uint32_t* __restric
         if (sb > smax && meta[2] <= MSM_MAX_GIANTS) sb = 0;
         if (sb < 2) sb = 0;
     }
+    // warp-uniform trip count: every lane must take part in the quad additions' shuffles
+    const unsigned my_trips = sb > gl ? (sb - gl + G - 1) / G : 0;
+    const unsigned trips = __reduce_max_sync(0xffffffffu, my_trips);
     xyzz_t acc = xyzz_identity();
-    for (uint32_t j = gl; j < sb; j += G) acc = xyzz_add<F>(acc, load_xyzz(partials + t0 + j));
+    for (unsigned k = 0; k < trips; k++) {
+        const uint32_t j = gl + k * G;
+        xyzz_t o = j < sb ? load_xyzz(partials + t0 + j) : xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
 #pragma unroll 1
     for (unsigned d = G >> 1; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, d);
-        if (gl < d) acc = xyzz_add<F>(acc, o);
+        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
+        if (gl >= d) o = xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
     }
-    if (gl == 0 && sb) store_xyzz(buckets + b, acc);
+    if (gl == 0 && sb && (threadIdx.x & 3) == 0) store_xyzz(buckets + b, acc);
 }
 
 // ---------------------------------------------------------------------------------------------- bucket reduction
 // sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of (b+1) set.
 // grid (blocks_per_bit, c, G); every CTA tree-sums its slice of one group's buckets for one bit.
-// Block-wide point sum through shared memory with re-compaction: after every level the live partials are the first
-// `stride` threads, so whole warps retire early and only the last five levels run with a partly filled warp (a shuffle
-// tree would keep every warp busy for five full additions).  blockDim.x must be a power of two <= TREE_THREADS.
-constexpr unsigned TREE_THREADS = 256;
-template <class F> __device__ __forceinline__ xyzz_t block_tree_sum(xyzz_t acc, xyzz_t* sm) {
-    const unsigned tid = threadIdx.x;
-    store_xyzz(sm + tid, acc);
-    __syncthreads();
-#pragma unroll 1
-    for (unsigned stride = blockDim.x >> 1; stride >= 1; stride >>= 1) {
-        if (tid < stride) {
-            acc = xyzz_add<F>(acc, load_xyzz(sm + tid + stride));
-            store_xyzz(sm + tid, acc);
-        }
-        __syncthreads();
-    }
-    return acc;  // valid in thread 0
-}
+constexpr unsigned TREE_THREADS = 256;              // 64 quads per CTA in the reduction kernels
+constexpr unsigned TREE_QUADS = TREE_THREADS / 4;
 
-// One CTA per giant bucket: strided serial sums of its partial list, then the block tree.
+// One CTA per giant bucket: its quads stride over the partial list, then the block tree (quad.cuh).
 template <class F>
 __global__ void __launch_bounds__(TREE_THREADS) k_giant_finish(const uint32_t* __restrict__ giants, const uint32_t* __restrict__ meta,
                                                                const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t K,
@@ -268,29 +262,39 @@ __global__ void __launch_bounds__(TREE_THREADS) k_giant_finish(const uint32_t* _
     if (ng > MSM_MAX_GIANTS || blockIdx.x >= ng) return;  // overflow: k_bucket_finish took them
     const uint32_t b = giants[blockIdx.x];
     const uint32_t nbk = offsets[b + 1] - offsets[b], sb = (nbk + K - 1) / K, t0 = task_off[b];
+    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
     xyzz_t acc = xyzz_identity();
-    for (uint32_t j = threadIdx.x; j < sb; j += blockDim.x) acc = xyzz_add<F>(acc, load_xyzz(partials + t0 + j));
-    acc = block_tree_sum<F>(acc, sm_tree);
+    for (uint32_t j0 = 0; j0 < sb; j0 += nq) {
+        xyzz_t o = j0 + qd < sb ? load_xyzz(partials + t0 + j0 + qd) : xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
     if (threadIdx.x == 0) store_xyzz(buckets + b, acc);
 }
 
 // sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of i = b+1 set, i in [1, B], B = 2^(c-1).
 // For t < c-1 exactly B/2 indices qualify; the j-th is i = (j >> t) << (t+1) | 1 << t | (j & (2^t - 1)).  Slice c-1 is the
-// single bucket i = B.  grid (blocks_per_bit, c-1, G): every CTA sums a contiguous range of j (coalesced runs of 2^t
-// buckets), a few per thread, then the block tree.
+// single bucket i = B.  grid (blocks_per_bit, c-1, G): every CTA sums a contiguous range of j, a few per quad, then the
+// block tree.
 template <class F>
-__global__ void __launch_bounds__(TREE_THREADS, 2) k_bitsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned c, xyzz_t* partial) {
+__global__ void __launch_bounds__(TREE_THREADS) k_bitsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned c, xyzz_t* partial) {
     extern __shared__ xyzz_t sm_tree[];
     const unsigned t = blockIdx.y, g = blockIdx.z, nblk = gridDim.x;
     const uint32_t half = B >> 1, per = (half + nblk - 1) / nblk;
     const uint32_t j0 = blockIdx.x * per, j1 = min(half, j0 + per);
     const xyzz_t* bk = buckets + (size_t)g * B;
+    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
     xyzz_t acc = xyzz_identity();
-    for (uint32_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-        uint32_t i = ((j >> t) << (t + 1)) | (1u << t) | (j & ((1u << t) - 1));
-        acc = xyzz_add<F>(acc, load_xyzz(bk + (i - 1)));
+    for (uint32_t jb = j0; jb < j1; jb += nq) {
+        const uint32_t j = jb + qd;
+        xyzz_t o = xyzz_identity();
+        if (j < j1) {
+            uint32_t i = ((j >> t) << (t + 1)) | (1u << t) | (j & ((1u << t) - 1));
+            o = load_xyzz(bk + (i - 1));
+        }
+        acc = xyzz_add_quad<F>(acc, o);
     }
-    acc = block_tree_sum<F>(acc, sm_tree);
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
     if (threadIdx.x == 0) store_xyzz(partial + ((size_t)g * c + t) * nblk + blockIdx.x, acc);
 }
 
@@ -300,13 +304,17 @@ __global__ void __launch_bounds__(64) k_bitsum_final(const xyzz_t* __restrict__ 
                                                      unsigned nblk, xyzz_t* out) {
     extern __shared__ xyzz_t sm_tree[];
     const unsigned g = blockIdx.x / c, t = blockIdx.x % c;
+    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
     xyzz_t acc = xyzz_identity();
     if (t == c - 1) {
-        if (threadIdx.x == 0) acc = load_xyzz(buckets + (size_t)g * B + (B - 1));
+        if (qd == 0) acc = load_xyzz(buckets + (size_t)g * B + (B - 1));
     } else {
-        for (unsigned j = threadIdx.x; j < nblk; j += blockDim.x) acc = xyzz_add<F>(acc, load_xyzz(partial + (size_t)blockIdx.x * nblk + j));
+        for (unsigned j0 = 0; j0 < nblk; j0 += nq) {
+            xyzz_t o = j0 + qd < nblk ? load_xyzz(partial + (size_t)blockIdx.x * nblk + j0 + qd) : xyzz_identity();
+            acc = xyzz_add_quad<F>(acc, o);
+        }
     }
-    acc = block_tree_sum<F>(acc, sm_tree);
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
     if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, acc);
 }
 
@@ -359,15 +367,17 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     const size_t NTmax = Mmax / K + NB + 1;           // sum_b ceil(n_b / K) <= M / K + (number of non-empty buckets)
     // lanes per bucket in the finish pass: ~a quarter of the expected partials per bucket
     const uint64_t s_avg = Mmax / ((uint64_t)K * NB) + 1;
-    unsigned log_g = pow2_ceil_log((s_avg + 3) / 4);
-    if (log_g > 5) log_g = 5;
+    unsigned log_g = pow2_ceil_log((s_avg + 7) / 8);   // quads per bucket in the finish pass
+    if (log_g > 3) log_g = 3;
     const uint32_t smax = 32u << log_g;               // more partials than this: the bucket is "giant"
-    // bit-sliced bucket sums: (c-1) slices of B/2 elements; elements per thread chosen so that all CTAs are resident at once
-    const unsigned bs_threads = (unsigned)std::min<uint32_t>(TREE_THREADS, std::max<uint32_t>(32, B / 2));
-    size_t per_thread = ((size_t)(c - 1) * (B / 2) * G + (size_t)ws.sm_count * 512 - 1) / ((size_t)ws.sm_count * 512);
-    if (per_thread < 2) per_thread = 2;
+    // bit-sliced bucket sums: (c-1) slices of B/2 elements; elements per quad chosen so that all CTAs are resident at once
+    unsigned bs_threads = TREE_THREADS;
+    while (bs_threads > 32 && bs_threads / 4 > B / 2) bs_threads /= 2;
+    const size_t resident_quads = (size_t)ws.sm_count * TREE_QUADS;            // one 256-thread CTA per SM (register bound)
+    size_t per_quad = ((size_t)(c - 1) * (B / 2) * G + resident_quads - 1) / resident_quads;
+    if (per_quad < 2) per_quad = 2;
     unsigned nblk = 1;
-    while (nblk < 64 && (size_t)nblk * 2 * bs_threads * per_thread <= B / 2) nblk *= 2;
+    while (nblk < 64 && (size_t)nblk * 2 * (bs_threads / 4) * per_quad <= B / 2) nblk *= 2;
 
     static_assert(sizeof(xyzz_t) == 128 && sizeof(affine_t) == 64 && sizeof(fe) == 32, "layout");
     // scratch, grouped by what sizes it: the entry list (n * nwin), the bucket array (G * B), the bit sums (G * c)
@@ -436,16 +446,16 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
                                                                    ws.d_buckets, ws.d_partials);
     STAGE_MARK(4);
     // 5. per-bucket sums of the task partials (+ giants)
-    k_bucket_finish<F><<<(unsigned)(((NB << log_g) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
+    k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
                                                                               ws.d_buckets, ws.d_partials);
-    k_giant_finish<F><<<MSM_MAX_GIANTS, TREE_THREADS, TREE_THREADS * sizeof(xyzz_t), st>>>(ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials);
+    k_giant_finish<F><<<MSM_MAX_GIANTS, TREE_THREADS, TREE_QUADS * sizeof(xyzz_t), st>>>(ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials);
     STAGE_MARK(5);
     // 6. bit-sliced bucket sums
     xyzz_t* d_partial = ws.d_bitsums;
     xyzz_t* d_T = ws.d_bitsums + (size_t)G * c * nblk;
     if (c > 1 && B >= 2)
-        k_bitsum<F><<<dim3(nblk, c - 1, G), bs_threads, bs_threads * sizeof(xyzz_t), st>>>(ws.d_buckets, B, c, d_partial);
-    k_bitsum_final<F><<<G * c, 64, 64 * sizeof(xyzz_t), st>>>(d_partial, ws.d_buckets, B, c, nblk, d_T);
+        k_bitsum<F><<<dim3(nblk, c - 1, G), bs_threads, (bs_threads / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, c, d_partial);
+    k_bitsum_final<F><<<G * c, 64, 16 * sizeof(xyzz_t), st>>>(d_partial, ws.d_buckets, B, c, nblk, d_T);
     nl += 8;
     STAGE_MARK(6);
     ZK_CUDA(cudaGetLastError());

@@ -78,7 +78,7 @@ void ntt_free_tables(NttTables& t) {
 // Shared-memory tile, limb-major: word (limb l, column c, row r) at sm[(l*T + c)*(S+1) + r].  Adjacent threads work on
 // adjacent rows of one column, so every layer is bank-conflict free; the +1 pitch keeps the column-fastest load/store
 // conflict free as well.
-template <class F> __global__ void __launch_bounds__(NTT_THREADS, 1) k_ntt_pass(NttPassParams p) {
+template <class F> __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(NttPassParams p) {
     extern __shared__ uint32_t sm[];
     const unsigned S = 1u << p.log_s, T = 1u << p.log_t, PITCH = S + 1;
     const unsigned tid = threadIdx.x;
@@ -179,7 +179,7 @@ static unsigned pick_log_t(unsigned log_s, size_t ncols, size_t batch) {
     size_t t = NTT_TILE_ELEMS >> log_s;
     if (t > ncols) t = ncols;
     if (t < 1) t = 1;
-    while (t > 4 && ((ncols + t - 1) / t) * batch < 2 * 148) t /= 2;
+    while (t > 2 && ((ncols + t - 1) / t) * batch < 3 * 148) t /= 2;
     unsigned l = 0;
     while (((size_t)1 << (l + 1)) <= t) l++;
     return l;

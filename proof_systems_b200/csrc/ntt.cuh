@@ -20,8 +20,8 @@ namespace zkb {
 
 constexpr unsigned NTT_MAX_LOG_SUB = 10;   // sub-transform size limit (shared-memory tile)
 constexpr unsigned NTT_MAX_LOG_N = 20;     // two passes of <= 2^10
-constexpr unsigned NTT_TILE_ELEMS = 4096;  // S*T elements per CTA tile (128 KiB of fe)
-constexpr unsigned NTT_THREADS = 512;
+constexpr unsigned NTT_TILE_ELEMS = 2048;  // S*T elements per CTA tile (64 KiB of fe): three CTAs per SM overlap each other's barriers
+constexpr unsigned NTT_THREADS = 256;
 
 // device tables of one (field, log_n, direction)
 struct NttTables {
