@@ -98,6 +98,11 @@ def cpu_time(fn, min_seconds, max_reps):
             return el / reps, reps
 
 
+def cpu_msm(orc, g, scalars, threads):
+    """what SRS::commit_non_hiding runs for a |g|-coefficient polynomial: two half MSMs under rayon::join, then add"""
+    return orc.msm_split2(orc.PALLAS, g, scalars, threads=threads)
+
+
 def run_reference(args):
     """The reference's CPU path for this workload, as restated by the oracle (oracle/pasta_oracle.c: ark-style signed-digit
     Pippenger with window-parallel threads; ark-style radix-2 FFT), all host threads."""
@@ -105,17 +110,17 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as orc
-    threads = orc.lib().orc_max_threads()
+    threads = orc.host_threads()
     g, scalars, poly = make_inputs(orc, 0)
     for _ in range(max(1, args.warmup)):
-        orc.msm(orc.PALLAS, g, scalars)
+        cpu_msm(orc, g, scalars, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.msm(orc.PALLAS, g, scalars)
+        cpu_msm(orc, g, scalars, threads)
     msm_s = (time.perf_counter() - t0) / args.steps
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.ntt(orc.FP, poly)
+        orc.ntt(orc.FP, poly, threads=threads)
     ntt_s = (time.perf_counter() - t0) / args.steps
     val = N_PTS / msm_s
     sample = f"{args.steps} x (one 2^16-point Pallas MSM, uniform scalars) after {max(1, args.warmup)} warm-up"
@@ -124,7 +129,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": msm_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (4 x u64 Montgomery limbs)", "data": "synthetic",
         "config": {"workload": "2^16-point Pallas MSM on srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)",
-                   "cpu_path": "oracle port of ark-ec 0.5 msm_bigint (reference is Rust; no cargo in the image)"},
+                   "cpu_path": "oracle port of ark-ec 0.5 msm_bigint under the reference's 2-way rayon::join split (ipa.rs:652-662); the reference is Rust and there is no cargo in the image"},
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ntt": {"metric": "fp_ntt_elements_per_s", "value": N_PTS / ntt_s, "unit": "elements/s", "ms": ntt_s * 1e3,
@@ -283,7 +288,7 @@ def main():
         return
 
     # ---- correctness of what was timed + CPU baseline on the same host (bounded sample)
-    threads = orc.lib().orc_max_threads()
+    threads = orc.host_threads()
     if world == 1:
         want = orc.msm(orc.PALLAS, g, scalars)
     else:
@@ -294,8 +299,8 @@ def main():
             tot = [(a + b) % m for a, b in zip(tot, sr)]
         want = orc.msm(orc.PALLAS, g, orc.ints_to_limbs(tot))
     ok = bool(np.array_equal(zk.jacobian_to_affine(zk.PALLAS, result), want))
-    cpu_msm_s, cpu_reps = cpu_time(lambda: orc.msm(orc.PALLAS, g, scalars), args.cpu_seconds, 50)
-    cpu_ntt_s, cpu_ntt_reps = cpu_time(lambda: orc.ntt(orc.FP, poly), args.cpu_seconds / 3, 200)
+    cpu_msm_s, cpu_reps = cpu_time(lambda: cpu_msm(orc, g, scalars, threads), args.cpu_seconds, 50)
+    cpu_ntt_s, cpu_ntt_reps = cpu_time(lambda: orc.ntt(orc.FP, poly, threads=threads), args.cpu_seconds / 3, 200)
 
     peak, peak_src = load_peaks()
     per_step_ms = msm_ms / args.steps
@@ -324,7 +329,7 @@ def main():
                      "note": "MSM is integer-ALU bound: 96 B/point of compulsory traffic vs ~16 mixed additions (160 modmul) per point",
                      "stage_ms": stages},
         "cpu_baseline": {"value": N_PTS / cpu_msm_s, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"{cpu_reps} x the same 2^16-point MSM (oracle: ark-style Pippenger, {threads} threads), {cpu_msm_s * 1e3:.1f} ms each"},
+                         "sample": f"{cpu_reps} x the same 2^16-point MSM (oracle: ark-style Pippenger, 2-way split, {threads} threads), {cpu_msm_s * 1e3:.1f} ms each"},
         "ntt": {
             "metric": "fp_ntt_elements_per_s", "workload": "2^16-element Fp forward NTT (Radix2EvaluationDomain::fft_in_place)" + ("" if world == 1 else f", {world} replicas"),
             "value": world * N_PTS / (ntt_ms / args.steps * 1e-3), "unit": "elements/s", "ms_per_step": ntt_ms / args.steps,

@@ -267,3 +267,34 @@ static int CN(decompress)(CN(aff) *r, const uint8_t in[33]) {
     r->y = (want_larger == y_is_larger) ? y : ny;
     return 1;
 }
+
+/*
+ * Deterministic extension of a base set for the synthetic large-MSM configs ("2^20 bases =
+ * srs/test_vesta.srs g[..] extended deterministically by batch-affine additions of earlier entries"):
+ *   out[0..m) = in;   out[k*m + i] = out[(k-1)*m + i] + in[(i + k) % m]        (one shared inversion per block of m)
+ * Any on-curve points are valid MSM bases; the oracle and the GPU run on the identical array.
+ */
+static void CN(extend_bases)(CN(aff) *out, const CN(aff) *in, size_t m, size_t n) {
+    memcpy(out, in, (m < n ? m : n) * sizeof(CN(aff)));
+    BF(t) *den = (BF(t) *)malloc(m * sizeof(BF(t)));
+    for (size_t k = 1; k * m < n; k++) {
+        size_t cnt = (k + 1) * m <= n ? m : n - k * m;
+        const CN(aff) *prev = out + (k - 1) * m;
+        CN(aff) *cur = out + k * m;
+        for (size_t i = 0; i < cnt; i++) BF(sub)(&den[i], &in[(i + k) % m].x, &prev[i].x);   /* x2 - x1 */
+        BF(batch_inv)(den, cnt);
+        for (size_t i = 0; i < cnt; i++) {
+            const CN(aff) *p = &prev[i], *q = &in[(i + k) % m];
+            if (BF(is_zero)(&den[i]) || CN(aff_is_inf)(p) || CN(aff_is_inf)(q)) {   /* same x or identity: generic law */
+                CN(jac) j; CN(jac_from_aff)(&j, p); CN(jac_add_mixed)(&j, &j, q); CN(jac_to_aff)(&cur[i], &j);
+                continue;
+            }
+            BF(t) lam, t, x3, y3;
+            BF(sub)(&t, &q->y, &p->y); BF(mul)(&lam, &t, &den[i]);
+            BF(sqr)(&x3, &lam); BF(sub)(&x3, &x3, &p->x); BF(sub)(&x3, &x3, &q->x);
+            BF(sub)(&t, &p->x, &x3); BF(mul)(&y3, &lam, &t); BF(sub)(&y3, &y3, &p->y);
+            cur[i].x = x3; cur[i].y = y3;
+        }
+    }
+    free(den);
+}

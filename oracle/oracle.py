@@ -77,7 +77,9 @@ def lib() -> ctypes.CDLL:
         L.orc_decompress.restype = sz
         L.orc_msm.argtypes = [i, u64p, u64p, sz, i, i, u64p, u64p]
         L.orc_msm_mont.argtypes = [i, u64p, u64p, sz, i, u64p]
+        L.orc_msm_split2.argtypes = [i, u64p, u64p, sz, i, u64p]
         L.orc_group_intt.argtypes = [i, u64p, u64p, u, i]
+        L.orc_extend_bases.argtypes = [i, u64p, sz, u64p, sz]
         _lib = L
     return _lib
 
@@ -272,6 +274,24 @@ def msm(cid, bases: np.ndarray, scalars: np.ndarray, algo: int = 0, threads: int
     return (aff, jac) if want_jac else aff
 
 
+def msm_split2(cid, bases, scalars, threads: int = 0) -> np.ndarray:
+    """commit_non_hiding's `len == |g|` branch (ipa.rs:652-662): rayon::join of two half MSMs, then add."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    n = min(bases.shape[0], scalars.shape[0])
+    aff = np.empty(8, dtype=np.uint64)
+    lib().orc_msm_split2(cid, _p(bases), _p(scalars), n, threads, _p(aff))
+    return aff
+
+
+def host_threads() -> int:
+    """threads the CPU baseline may use: the cores this process is allowed on (torchrun pins OMP_NUM_THREADS=1)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def msm_mont(cid, bases, scalars_mont, threads: int = 0) -> np.ndarray:
     """G::Group::msm(bases, scalars).unwrap().into_affine(); scalars Montgomery."""
     bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
@@ -280,6 +300,14 @@ def msm_mont(cid, bases, scalars_mont, threads: int = 0) -> np.ndarray:
     aff = np.empty(8, dtype=np.uint64)
     lib().orc_msm_mont(cid, _p(bases), _p(scalars_mont), bases.shape[0], threads, _p(aff))
     return aff
+
+
+def extend_bases(cid, points: np.ndarray, n: int) -> np.ndarray:
+    """Deterministic n-point base set from m fixture points (block k = block k-1 + rotated fixture; batch-affine)."""
+    pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+    out = np.empty((n, 8), dtype=np.uint64)
+    lib().orc_extend_bases(cid, _p(pts), pts.shape[0], _p(out), n)
+    return out
 
 
 def group_intt(cid, points: np.ndarray, threads: int = 0) -> np.ndarray:

@@ -191,6 +191,11 @@ EXPORT size_t orc_decompress(int cid, const uint8_t *in, uint64_t *out, size_t n
     return ok;
 }
 
+EXPORT void orc_extend_bases(int cid, const uint64_t *in, size_t m, uint64_t *out, size_t n) {
+    if (cid == 0) pallas_extend_bases((pallas_aff *)out, (const pallas_aff *)in, m, n);
+    else vesta_extend_bases((vesta_aff *)out, (const vesta_aff *)in, m, n);
+}
+
 /* MSM == G::Group::msm_bigint(bases, scalars): scalars canonical.  out_jac: 12 u64 (may be NULL),
  * out_aff: 8 u64 (may be NULL).  algo 0 = Pippenger (ark-like), 1 = naive definition. */
 EXPORT void orc_msm(int cid, const uint64_t *bases, const uint64_t *scalars, size_t n, int algo, int threads,
@@ -209,6 +214,28 @@ EXPORT void orc_msm(int cid, const uint64_t *bases, const uint64_t *scalars, siz
         if (out_jac) memcpy(out_jac, &r, sizeof r);
         if (out_aff) vesta_jac_to_aff((vesta_aff *)out_aff, &r);
     }
+}
+
+/* The reference's commit_non_hiding for a polynomial of exactly |g| coefficients (poly-commitment/src/ipa.rs:652-662):
+ * rayon::join of two half-size MSMs, then one addition — the "vertical" split benchmarked in benches/msm.rs:71-88.
+ * Each half gets half of the threads (windows in parallel inside, like rayon's nested work-stealing). */
+EXPORT void orc_msm_split2(int cid, const uint64_t *bases, const uint64_t *scalars, size_t n, int threads, uint64_t *out_aff) {
+    threads = default_threads(threads);
+    int th = threads / 2 > 0 ? threads / 2 : 1;
+    size_t h = n / 2;
+    uint64_t j0[12], j1[12], sum[12];
+#ifdef _OPENMP
+    omp_set_max_active_levels(2);
+#endif
+#pragma omp parallel sections num_threads(2)
+    {
+#pragma omp section
+        orc_msm(cid, bases, scalars, h, 0, th, j0, NULL);
+#pragma omp section
+        orc_msm(cid, bases + 8 * h, scalars + 4 * h, n - h, 0, th, j1, NULL);
+    }
+    orc_jac_add(cid, j0, j1, sum);
+    orc_jac_to_affine(cid, sum, out_aff);
 }
 
 /* == G::Group::msm(bases, scalars): scalars in Montgomery form (into_bigint first, like

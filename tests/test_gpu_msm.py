@@ -144,3 +144,25 @@ def test_batch_shares_bases(ctx, orc, vesta_srs):
     for j in range(k):
         assert np.array_equal(zk.jacobian_to_affine(srs.cid, out[j]), orc.msm(srs.cid, srs.g[:n], sc[j])), j
     bases.free()
+
+
+def test_config4_2_20_vesta_sharded(ctx, orc, vesta_srs):
+    """BASELINE config 4: 2^20-point Vesta MSM (fixture generators extended deterministically), uniform
+    Fp scalars seed 3.  The full MSM must match the oracle, and the per-shard partials of a 1/2/4/8-way split by points
+    (what ranks compute before the all-gather) must sum to the identical affine point."""
+    srs = vesta_srs
+    n = 1 << 20
+    g = orc.extend_bases(srs.cid, srs.g, n)
+    sc = orc.random_scalars(srs.scalar, n, seed=3)
+    want = orc.msm(srs.cid, g, sc)
+    bases = ctx.upload_bases(srs.cid, g, window_bits=-1)
+    assert bases.window_bits == 16
+    assert np.array_equal(ctx.msm_affine(bases, sc), want)
+    from proof_systems_b200.parallel import shard_bounds
+    for world in (2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_bounds(n, world, r)
+            parts.append(ctx.msm(bases, sc[lo:hi], off=lo))
+        assert np.array_equal(zk.jacobian_to_affine(srs.cid, zk.jacobian_sum(srs.cid, np.stack(parts))), want), world
+    bases.free()

@@ -169,6 +169,21 @@ def test_pippenger_edge_cases_vs_definition(orc, cid, pallas_srs, vesta_srs):
     # all-zero scalars and empty input -> identity
     assert not np.any(orc.msm(cid, g[:8], np.zeros((8, 4), dtype=np.uint64)))
     assert not np.any(orc.msm(cid, g[:0], sc[:0]))
+    # the reference's 2-way split (ipa.rs:652-662) gives the same group element
+    assert np.array_equal(orc.msm_split2(cid, srs.g[:2048], orc.random_scalars(srs.scalar, 2048, seed=4), threads=4),
+                          orc.msm(cid, srs.g[:2048], orc.random_scalars(srs.scalar, 2048, seed=4)))
     # thread count does not change the result
     big_sc = orc.random_scalars(srs.scalar, 2048, seed=4)
     assert np.array_equal(orc.msm(cid, srs.g[:2048], big_sc, threads=1), orc.msm(cid, srs.g[:2048], big_sc, threads=4))
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_extend_bases_are_curve_points_and_deterministic(orc, request, name):
+    srs = request.getfixturevalue(name)
+    ext = orc.extend_bases(srs.cid, srs.g[:64], 300)
+    assert np.array_equal(ext[:64], srs.g[:64])
+    assert all(orc.on_curve(srs.cid, p) for p in ext)
+    for k, i in [(1, 0), (2, 5), (4, 43)]:
+        assert np.array_equal(ext[k * 64 + i], orc.affine_add(srs.cid, ext[(k - 1) * 64 + i], srs.g[(i + k) % 64]))
+    assert len({p.tobytes() for p in ext}) == 300          # no repeats
+    assert np.array_equal(orc.extend_bases(srs.cid, srs.g[:64], 300), ext)
