@@ -15,8 +15,9 @@
  * entries, log n butterfly layers parallelised per layer, one bit-reversal permutation.
  */
 
-static void FN(bitrev_permute)(FN(t) *a, unsigned log_n) {
+static void FN(bitrev_permute)(FN(t) *a, unsigned log_n, int threads) {
     size_t n = (size_t)1 << log_n;
+#pragma omp parallel for num_threads(threads) schedule(static) if (n >= 65536 && threads > 1)
     for (size_t i = 0; i < n; i++) {
         size_t r = 0;
         for (unsigned b = 0; b < log_n; b++) r |= ((i >> b) & 1) << (log_n - 1 - b);
@@ -47,22 +48,40 @@ static void FN(ntt_core)(FN(t) *a, unsigned log_n, const FN(t) *w, int threads) 
         }
         free(starts);
     }
-    /* decimation in frequency: natural in, bit-reversed out */
+    /* decimation in frequency: natural in, bit-reversed out.  Layers with few, long groups are split along j, layers with
+     * many short groups along the groups (what ark-poly's per-layer chunking amounts to); threads are capped so that
+     * every thread gets at least 2048 butterflies per layer. */
+    int thr = threads;
+    if ((size_t)thr > n / 4096 + 1) thr = (int)(n / 4096 + 1);
     for (unsigned s = 0; s < log_n; s++) {
         size_t half = n >> (s + 1);        /* butterfly span */
-        size_t step = (size_t)1 << s;      /* root stride */
-#pragma omp parallel for num_threads(threads) schedule(static) if (n >= 4096)
-        for (size_t k = 0; k < n / 2; k++) {
-            size_t grp = k / half, j = k % half;
-            size_t i0 = grp * 2 * half + j, i1 = i0 + half;
-            FN(t) u = a[i0], v = a[i1], d;
-            FN(add)(&a[i0], &u, &v);
-            FN(sub)(&d, &u, &v);
-            FN(mul)(&a[i1], &d, &roots[j * step]);
+        size_t step = (size_t)1 << s;      /* root stride; also the number of groups */
+        if (step >= (size_t)thr * 4) {
+#pragma omp parallel for num_threads(thr) schedule(static) if (thr > 1)
+            for (size_t grp = 0; grp < step; grp++) {
+                FN(t) *lo = a + grp * 2 * half, *hi = lo + half;
+                for (size_t j = 0; j < half; j++) {
+                    FN(t) u = lo[j], v = hi[j], d;
+                    FN(add)(&lo[j], &u, &v);
+                    FN(sub)(&d, &u, &v);
+                    FN(mul)(&hi[j], &d, &roots[j * step]);
+                }
+            }
+        } else {
+            for (size_t grp = 0; grp < step; grp++) {
+                FN(t) *lo = a + grp * 2 * half, *hi = lo + half;
+#pragma omp parallel for num_threads(thr) schedule(static) if (thr > 1)
+                for (size_t j = 0; j < half; j++) {
+                    FN(t) u = lo[j], v = hi[j], d;
+                    FN(add)(&lo[j], &u, &v);
+                    FN(sub)(&d, &u, &v);
+                    FN(mul)(&hi[j], &d, &roots[j * step]);
+                }
+            }
         }
     }
     free(roots);
-    FN(bitrev_permute)(a, log_n);
+    FN(bitrev_permute)(a, log_n, thr);
 }
 
 static void FN(ntt)(FN(t) *a, unsigned log_n, int inverse, int coset, int threads) {

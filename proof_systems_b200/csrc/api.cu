@@ -10,6 +10,7 @@
 #include "host_field.hpp"
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "quad.cuh"
 
 namespace zkb {
 
@@ -164,6 +165,20 @@ template <class F> __global__ void k_madd_chain(xyzz_t* out, unsigned iters) {
     for (unsigned i = 0; i < iters; i++) {
         acc = xyzz_madd<F>(acc, q);
         q.x.v[3] ^= acc.X.v[0];   // data-dependent operand so nothing is hoisted
+    }
+    if (acc.X.v[0] == 0x12345678u && acc.ZZ.v[7] == 0x9abcdef0u) store_xyzz(out, acc);
+}
+
+// chains of full XYZZ additions: serial formula (kind 102) and the quad-cooperative one (kind 101)
+template <class F, int QUAD> __global__ void k_add_chain(xyzz_t* out, unsigned iters) {
+    affine_t q;
+    q.x = fe_one<F>(); q.y = fe_r2<F>();
+    q.x.v[0] ^= QUAD ? (threadIdx.x >> 2) : threadIdx.x; q.y.v[1] ^= blockIdx.x;
+    xyzz_t acc = xyzz_from_affine<F>(q), b = acc;
+    b.X.v[2] ^= 0x55u; b.ZZ.v[1] ^= 0x3u;
+    for (unsigned i = 0; i < iters; i++) {
+        acc = QUAD ? xyzz_add_quad<F>(acc, b) : xyzz_add<F>(acc, b);
+        b.X.v[3] ^= acc.X.v[0];
     }
     if (acc.X.v[0] == 0x12345678u && acc.ZZ.v[7] == 0x9abcdef0u) store_xyzz(out, acc);
 }
@@ -425,6 +440,8 @@ int zk_debug_op_throughput(zk_ctx* ctx, int field_id, int kind, unsigned blocks,
         if (kind == 1) k_mul_chain<F, 1><<<blocks, threads, 0, ctx->stream>>>((fe*)dout, iters);         \
         else if (kind == 2) k_mul_chain<F, 2><<<blocks, threads, 0, ctx->stream>>>((fe*)dout, iters);    \
         else if (kind == 4) k_mul_chain<F, 4><<<blocks, threads, 0, ctx->stream>>>((fe*)dout, iters);    \
+        else if (kind == 101) k_add_chain<F, 1><<<blocks, threads, 0, ctx->stream>>>(dout, iters);                \
+        else if (kind == 102) k_add_chain<F, 0><<<blocks, threads, 0, ctx->stream>>>(dout, iters);                \
         else k_madd_chain<F><<<blocks, threads, 0, ctx->stream>>>(dout, iters);
         if (field_id == ZK_FP) { LAUNCH(FpParams) } else { LAUNCH(FqParams) }
 #undef LAUNCH
@@ -435,7 +452,7 @@ int zk_debug_op_throughput(zk_ctx* ctx, int field_id, int kind, unsigned blocks,
     ctx->launches += 2;
     float ms = 0;
     ZK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    double per_thread = kind == 100 ? 1.0 : (double)kind;
+    double per_thread = kind == 101 ? 0.25 : kind >= 100 ? 1.0 : (double)kind;
     *out_ops_per_s = per_thread * iters * (double)blocks * threads / (ms * 1e-3);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dout);
     return ZK_OK;

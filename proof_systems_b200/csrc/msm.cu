@@ -211,6 +211,24 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
     store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
 }
 
+// Thread-per-bucket variant of the finish pass, for MANY buckets with few partials each: with more buckets than resident
+// quads the pass is throughput bound and the serial formula (one thread per addition) is the cheaper way to spend lanes.
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_finish_serial(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
+                                                              uint32_t K, uint32_t smax, const uint32_t* __restrict__ meta, xyzz_t* buckets,
+                                                              const xyzz_t* __restrict__ partials) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t nbk = __ldg(offsets + b + 1) - __ldg(offsets + b);
+    uint32_t sb = (nbk + K - 1) / K;
+    if (sb > smax && meta[2] <= MSM_MAX_GIANTS) return;  // k_giant_finish
+    if (sb < 2) return;                                  // 0: empty, 1: written by k_accumulate
+    const xyzz_t* p = partials + __ldg(task_off + b);
+    xyzz_t acc = load_xyzz(p);
+    for (uint32_t j = 1; j < sb; j++) acc = xyzz_add<F>(acc, load_xyzz(p + j));
+    store_xyzz(buckets + b, acc);
+}
+
 // Buckets with 2 <= s_b <= smax tasks: a group of G = 2^log_g QUADS (quad.cuh) sums the bucket's partials — strided serial
 // part, then a shuffle tree over the quads of the group.  One quad per bucket when buckets hold only a few partials.
 template <class F>
@@ -356,11 +374,15 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     // Entries per accumulation task: the accumulate kernel keeps `capacity` threads resident (4 CTAs of 128 per SM at
     // <= 128 registers); K is chosen so that the tasks fill a whole number of waves (a 1.02-wave grid costs two waves).
     const size_t capacity = (size_t)ws.sm_count * 512;
+    const size_t resident_quads = (size_t)ws.sm_count * TREE_QUADS;
+    const bool serial_finish = NB > resident_quads;   // many small buckets: throughput regime (see k_bucket_finish_serial)
     uint32_t K = ws.chunk;
     if (K == 0) {
         const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
         size_t waves = (Mmax + 24 * capacity - 1) / (24 * capacity);
         if (waves == 0) waves = 1;
+        // a cheap finish pass affords twice as many (half as long, better balanced) tasks
+        if (serial_finish && Mmax / (2 * waves * capacity) >= 6) waves *= 2;
         K = (uint32_t)((Mmax + waves * capacity - slack - 1) / (waves * capacity - slack));
         if (K < 4) K = 4;
     }
@@ -373,7 +395,6 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     // bit-sliced bucket sums: (c-1) slices of B/2 elements; elements per quad chosen so that all CTAs are resident at once
     unsigned bs_threads = TREE_THREADS;
     while (bs_threads > 32 && bs_threads / 4 > B / 2) bs_threads /= 2;
-    const size_t resident_quads = (size_t)ws.sm_count * TREE_QUADS;            // one 256-thread CTA per SM (register bound)
     size_t per_quad = ((size_t)(c - 1) * (B / 2) * G + resident_quads - 1) / resident_quads;
     if (per_quad < 2) per_quad = 2;
     unsigned nblk = 1;
@@ -446,8 +467,11 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
                                                                    ws.d_buckets, ws.d_partials);
     STAGE_MARK(4);
     // 5. per-bucket sums of the task partials (+ giants)
-    k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
-                                                                              ws.d_buckets, ws.d_partials);
+    if (serial_finish)
+        k_bucket_finish_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, ws.d_buckets, ws.d_partials);
+    else
+        k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
+                                                                                  ws.d_buckets, ws.d_partials);
     k_giant_finish<F><<<MSM_MAX_GIANTS, TREE_THREADS, TREE_QUADS * sizeof(xyzz_t), st>>>(ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials);
     STAGE_MARK(5);
     // 6. bit-sliced bucket sums
