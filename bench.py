@@ -33,6 +33,11 @@ MSM_BYTES_PER_POINT = 96      # 64 B affine base + 32 B scalar
 NTT_BYTES_PER_ELEM = 64       # 32 B read + 32 B write per transform
 
 
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,6 +308,10 @@ def main():
     cpu_ntt_s, cpu_ntt_reps = cpu_time(lambda: orc.ntt(orc.FP, poly, threads=threads), args.cpu_seconds / 3, 200)
 
     peak, peak_src = load_peaks()
+    traffic = load_traffic()
+    msm_traffic = traffic.get("k_accumulate", {}).get("bytes_per_launch") if wb == 15 else None   # captured at window 15 only
+    ntt_traffic = traffic.get("k_ntt_pass", {})
+    ntt_traffic = ntt_traffic.get("bytes_per_launch", 0) * ntt_traffic.get("launches_per_transform", 0) or None
     per_step_ms = msm_ms / args.steps
     value = world * N_PTS / (per_step_ms * 1e-3)
     e2e_value = world * N_PTS / (msm_e2e_ms / args.steps * 1e-3)
@@ -325,8 +334,10 @@ def main():
         "gpu_launches": int(launches_total),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_accumulate (bucket accumulation)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acc,
-                     "note": "MSM is integer-ALU bound: 96 B/point of compulsory traffic vs ~16 mixed additions (160 modmul) per point",
+                     "frac": achieved / peak, "traffic": msm_traffic, "peak_source": peak_src, "kernel_ms": acc,
+                     "algorithmic_bytes": MSM_BYTES_PER_POINT * N_PTS,
+                     "note": "MSM is integer-ALU bound: 96 B/point of compulsory traffic vs ~17 mixed additions (~200 modular multiplications) per point; "
+                             "the accumulation kernel gathers 64 B per (point, window) from the resident table, which is what `traffic` shows",
                      "stage_ms": stages},
         "cpu_baseline": {"value": N_PTS / cpu_msm_s, "unit": "points/s", "cores": threads, "kind": "port",
                          "sample": f"{cpu_reps} x the same 2^16-point MSM (oracle: ark-style Pippenger, 2-way split, {threads} threads), {cpu_msm_s * 1e3:.1f} ms each"},
@@ -334,7 +345,8 @@ def main():
             "metric": "fp_ntt_elements_per_s", "workload": "2^16-element Fp forward NTT (Radix2EvaluationDomain::fft_in_place)" + ("" if world == 1 else f", {world} replicas"),
             "value": world * N_PTS / (ntt_ms / args.steps * 1e-3), "unit": "elements/s", "ms_per_step": ntt_ms / args.steps,
             "e2e": {"value": world * N_PTS / (ntt_e2e_ms / args.steps * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": N_PTS * 32, "d2h_bytes_per_step": N_PTS * 32},
-            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass x2", "achieved": ntt_ach, "peak": peak, "unit": "GB/s", "frac": ntt_ach / peak, "traffic": None, "kernel_ms": ntt_k},
+            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass x2", "achieved": ntt_ach, "peak": peak, "unit": "GB/s", "frac": ntt_ach / peak, "traffic": ntt_traffic, "kernel_ms": ntt_k,
+                         "algorithmic_bytes": NTT_BYTES_PER_ELEM * N_PTS},
             "cpu_baseline": {"value": N_PTS / cpu_ntt_s, "unit": "elements/s", "cores": threads, "kind": "port", "sample": f"{cpu_ntt_reps} x the same transform"},
         },
     }

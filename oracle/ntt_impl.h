@@ -40,7 +40,7 @@ static void FN(ntt_core)(FN(t) *a, unsigned log_n, const FN(t) *w, int threads) 
         FN(t) *starts = (FN(t) *)malloc(nblk * sizeof(FN(t)));
         FN(set_one)(&starts[0]);
         for (size_t b = 1; b < nblk; b++) FN(mul)(&starts[b], &starts[b - 1], &wblk);
-#pragma omp parallel for num_threads(threads) schedule(static)
+#pragma omp parallel for num_threads(threads > 32 ? 32 : threads) schedule(static)
         for (size_t b = 0; b < nblk; b++) {
             FN(t) cur = starts[b];
             size_t end = (b + 1) * blk < half ? (b + 1) * blk : half;
@@ -48,35 +48,29 @@ static void FN(ntt_core)(FN(t) *a, unsigned log_n, const FN(t) *w, int threads) 
         }
         free(starts);
     }
-    /* decimation in frequency: natural in, bit-reversed out.  Layers with few, long groups are split along j, layers with
-     * many short groups along the groups (what ark-poly's per-layer chunking amounts to); threads are capped so that
-     * every thread gets at least 2048 butterflies per layer. */
+    /* decimation in frequency: natural in, bit-reversed out.  One parallel region per layer: the n/2 butterflies of a
+     * layer, indexed k = grp * half + j, are cut into contiguous chunks (what ark-poly's per-layer chunking amounts to).
+     * Threads are capped: at least 4096 butterflies per thread and layer, at most 32 threads (the transform is memory bound
+     * beyond that; oversubscribing a 128-thread host only adds barrier cost). */
     int thr = threads;
-    if ((size_t)thr > n / 4096 + 1) thr = (int)(n / 4096 + 1);
+    if (thr > 32) thr = 32;
+    if ((size_t)thr > n / 8192 + 1) thr = (int)(n / 8192 + 1);
+    const size_t total = n / 2;
+    const size_t nchunks = (size_t)thr * 4 < total ? (size_t)thr * 4 : 1;
     for (unsigned s = 0; s < log_n; s++) {
-        size_t half = n >> (s + 1);        /* butterfly span */
-        size_t step = (size_t)1 << s;      /* root stride; also the number of groups */
-        if (step >= (size_t)thr * 4) {
+        const size_t half = n >> (s + 1);        /* butterfly span */
+        const size_t step = (size_t)1 << s;      /* root stride; also the number of groups */
 #pragma omp parallel for num_threads(thr) schedule(static) if (thr > 1)
-            for (size_t grp = 0; grp < step; grp++) {
-                FN(t) *lo = a + grp * 2 * half, *hi = lo + half;
-                for (size_t j = 0; j < half; j++) {
-                    FN(t) u = lo[j], v = hi[j], d;
-                    FN(add)(&lo[j], &u, &v);
-                    FN(sub)(&d, &u, &v);
-                    FN(mul)(&hi[j], &d, &roots[j * step]);
-                }
-            }
-        } else {
-            for (size_t grp = 0; grp < step; grp++) {
-                FN(t) *lo = a + grp * 2 * half, *hi = lo + half;
-#pragma omp parallel for num_threads(thr) schedule(static) if (thr > 1)
-                for (size_t j = 0; j < half; j++) {
-                    FN(t) u = lo[j], v = hi[j], d;
-                    FN(add)(&lo[j], &u, &v);
-                    FN(sub)(&d, &u, &v);
-                    FN(mul)(&hi[j], &d, &roots[j * step]);
-                }
+        for (size_t ch = 0; ch < nchunks; ch++) {
+            size_t k0 = total * ch / nchunks, k1 = total * (ch + 1) / nchunks;
+            size_t grp = k0 / half, j = k0 % half;
+            for (size_t k = k0; k < k1; k++) {
+                FN(t) *lo = a + grp * 2 * half + j, *hi = lo + half;
+                FN(t) u = *lo, v = *hi, d;
+                FN(add)(lo, &u, &v);
+                FN(sub)(&d, &u, &v);
+                FN(mul)(hi, &d, &roots[j * step]);
+                if (++j == half) { j = 0; grp++; }
             }
         }
     }
