@@ -124,6 +124,11 @@ int zk_srs_create(zk_ctx* ctx, int curve_id, const uint64_t* g_xy, size_t n, con
 void zk_srs_destroy(zk_srs* srs);
 size_t zk_srs_max_poly_size(const zk_srs* srs);
 int zk_srs_add_lagrange_basis(zk_srs* srs, size_t domain_size, const uint64_t* basis_xy, int window_bits);
+/* SRS::get_lagrange_basis_from_domain_size -> SRS::lagrange_basis (ipa.rs:780-788, 1065-1172) computed ON THE DEVICE from the
+ * resident generators: inverse FFT over group elements + normalisation, registered for commit_evaluations_non_hiding.
+ * domain_size: power of two <= |g| (single-chunk bases).  zk_srs_get_lagrange_basis copies it to the host (n x 8 u64). */
+int zk_srs_lagrange_basis(zk_srs* srs, size_t domain_size, int window_bits);
+int zk_srs_get_lagrange_basis(zk_srs* srs, size_t domain_size, uint64_t* out_xy, size_t capacity_points);
 int zk_srs_commit_non_hiding(zk_srs* srs, const uint64_t* coeffs_mont, size_t len, size_t num_chunks, uint64_t* out_xy,
                              size_t out_capacity, size_t* out_chunks);
 int zk_srs_commit_evaluations_non_hiding(zk_srs* srs, size_t domain_size, const uint64_t* evals_mont,

@@ -81,4 +81,7 @@ template <class F, class FS>
 int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, bool scalars_mont, unsigned c, MsmWorkspace& ws,
             cudaStream_t st, MsmResultShape* shape, unsigned* launches);
 
+// group_ntt.cu: Lagrange-basis commitments of the domain of size 2^log_n from the resident generators (SRS::lagrange_basis)
+template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigned log_n, affine_t* d_out, cudaStream_t st, unsigned* launches);
+
 }  // namespace zkb

@@ -14,6 +14,7 @@
 #include "../../include/zkb200.h"
 #include "ctx.hpp"
 #include "host_field.hpp"
+#include "msm.cuh"
 
 using namespace zkb;
 
@@ -74,6 +75,48 @@ int zk_srs_add_lagrange_basis(zk_srs* srs, size_t domain_size, const uint64_t* b
     auto it = srs->lagrange.find(domain_size);
     if (it != srs->lagrange.end()) { zk_bases_free(it->second); it->second = b; }
     else srs->lagrange.emplace(domain_size, b);
+    return ZK_OK;
+}
+
+// SRS::get_lagrange_basis_from_domain_size (ipa.rs:780-788) -> SRS::lagrange_basis (ipa.rs:1065-1172), on the device:
+// group iFFT of g[0..domain_size) + normalisation; the basis is registered (with its window table) for
+// commit_evaluations_non_hiding.  Already registered sizes return at once, like the reference's cache.
+int zk_srs_lagrange_basis(zk_srs* srs, size_t domain_size, int window_bits) {
+    if (!srs || domain_size == 0 || (domain_size & (domain_size - 1))) { zk_set_error("lagrange_basis: domain size must be a power of two"); return ZK_ERR_INVALID; }
+    if (srs->lagrange.count(domain_size)) return ZK_OK;
+    if (domain_size > srs->n) { zk_set_error("lagrange_basis: chunked bases (domain %zu > srs %zu) are not on the device path yet", domain_size, srs->n); return ZK_ERR_INVALID; }
+    unsigned log_n = 0;
+    while (((size_t)1 << log_n) < domain_size) log_n++;
+    zk_ctx* ctx = srs->ctx;
+    affine_t* d_out = nullptr;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ZK_CUDA(cudaSetDevice(ctx->device));
+        ZK_CUDA(cudaMalloc(&d_out, domain_size * sizeof(affine_t)));
+        unsigned nl = 0;
+        rc = srs->curve == ZK_PALLAS ? lagrange_basis_build<FpParams, FqParams>(srs->g->b, log_n, d_out, ctx->stream, &nl)
+                                     : lagrange_basis_build<FqParams, FpParams>(srs->g->b, log_n, d_out, ctx->stream, &nl);
+        ctx->launches += nl;
+    }
+    if (rc == ZK_OK) {
+        zk_bases* b = nullptr;
+        rc = zk_bases_upload(ctx, srs->curve, (const uint64_t*)d_out, domain_size, window_bits, /*points_on_device=*/1, &b);
+        if (rc == ZK_OK) srs->lagrange.emplace(domain_size, b);
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+// Copy a registered basis back to the host (affine, n x 8 u64): what get_lagrange_basis(domain) derefs to.
+int zk_srs_get_lagrange_basis(zk_srs* srs, size_t domain_size, uint64_t* out_xy, size_t capacity_points) {
+    if (!srs || !out_xy) { zk_set_error("get_lagrange_basis: null argument"); return ZK_ERR_INVALID; }
+    auto it = srs->lagrange.find(domain_size);
+    if (it == srs->lagrange.end()) { zk_set_error("get_lagrange_basis: no basis for domain size %zu", domain_size); return ZK_ERR_INVALID; }
+    if (capacity_points < domain_size) { zk_set_error("get_lagrange_basis: capacity %zu < %zu", capacity_points, domain_size); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(srs->ctx->mu);
+    ZK_CUDA(cudaSetDevice(srs->ctx->device));
+    ZK_CUDA(cudaMemcpy(out_xy, it->second->b.d_points, domain_size * sizeof(affine_t), cudaMemcpyDeviceToHost));
     return ZK_OK;
 }
 

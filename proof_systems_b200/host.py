@@ -66,6 +66,14 @@ class SRS:
         assert b.shape[0] == domain_size
         check(lib().zk_srs_add_lagrange_basis(self._h, domain_size, _ptr(b), window_bits))
 
+    # fn get_lagrange_basis_from_domain_size(&self, domain_size: usize) -> &Vec<PolyComm<G>>
+    def get_lagrange_basis_from_domain_size(self, domain_size: int, window_bits: int = -1) -> np.ndarray:
+        """Computes (once) the basis on the device — SRS::lagrange_basis, ipa.rs:1065-1172 — and returns it: [n, 8] affine."""
+        check(lib().zk_srs_lagrange_basis(self._h, domain_size, window_bits))
+        out = np.empty((domain_size, 8), dtype=np.uint64)
+        check(lib().zk_srs_get_lagrange_basis(self._h, domain_size, out.ctypes.data_as(_u64p), domain_size))
+        return out
+
     # fn commit_non_hiding(&self, plnm: &DensePolynomial<F>, num_chunks: usize) -> PolyComm<G>
     def commit_non_hiding(self, coeffs, num_chunks: int) -> PolyComm:
         c = _np_u64(coeffs, (4,)) if len(coeffs) else np.zeros((0, 4), dtype=np.uint64)
