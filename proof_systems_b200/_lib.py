@@ -196,6 +196,16 @@ class Context:
         check(lib().zk_ntt_batch(self._h, field, _ptr(a), log_n, batch, in_len, int(inverse), int(coset)))
         return a
 
+    def ntt_inplace(self, field: int, a: np.ndarray, inverse: bool = False, coset: bool = False, in_len: int = 0):
+        """In-place transform of a C-contiguous uint64 array [n,4] or [batch,n,4] (e.g. a view of pinned memory): no copy
+        on the Python side, exactly the zk_ntt_batch call a Rust caller makes on its own Vec."""
+        assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"] and a.shape[-1] == 4
+        n = a.shape[-2]
+        batch = 1 if a.ndim == 2 else a.shape[0]
+        log_n = n.bit_length() - 1
+        assert 1 << log_n == n
+        check(lib().zk_ntt_batch(self._h, field, _ptr(a), log_n, batch, in_len, int(inverse), int(coset)))
+
     def ntt_dev(self, field: int, d_data: int, log_n: int, batch: int = 1, in_len: int = 0, inverse: bool = False, coset: bool = False):
         check(lib().zk_ntt_dev(self._h, field, ctypes.c_void_p(d_data), log_n, batch, in_len, int(inverse), int(coset)))
 

@@ -78,10 +78,12 @@ __global__ void k_recode(const fe* scalars, int scalars_mont, size_t n, unsigned
         if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
         else { sd = (int32_t)d; carry = 0; }
         digits[(size_t)w * n + i] = sd;
-        if (sd != 0) {
-            uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
-            atomicAdd(&counts[(groups_per_window ? w : 0) * B + (mag - 1)], 1u);
-        }
+        // warp-aggregated histogram update: lanes that hit the same bucket (kimchi's all-ones columns: all of them) elect
+        // one lane to add their count — one atomic per distinct bucket per warp instead of one per lane
+        const uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
+        const uint32_t key = sd != 0 ? (groups_per_window ? w : 0) * B + (mag - 1) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(__activemask(), key);
+        if (sd != 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
     }
 }
 
@@ -159,15 +161,21 @@ __global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offse
 __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned nwin, unsigned groups_per_window, size_t base_off,
                           size_t table_stride, int use_table, const uint32_t* offsets, uint32_t* cursors, uint32_t* entries) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n * nwin) return;
-    int32_t sd = digits[id];
-    if (sd == 0) return;
+    const bool in_range = id < n * nwin;
+    int32_t sd = in_range ? digits[id] : 0;
     unsigned w = (unsigned)(id / n);
     size_t i = id - (size_t)w * n;
     const uint32_t B = 1u << (c - 1);
     uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
-    uint32_t key = (groups_per_window ? w : 0) * B + (mag - 1);
-    uint32_t pos = offsets[key] + atomicAdd(&cursors[key], 1u);
+    uint32_t key = sd != 0 ? (groups_per_window ? w : 0) * B + (mag - 1) : 0xffffffffu;
+    // warp-aggregated cursor bump (see k_recode): the leader reserves a run, every peer takes its rank inside it
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const unsigned lane = threadIdx.x & 31, leader = (unsigned)(__ffs(peers) - 1);
+    uint32_t base = 0;
+    if (sd != 0 && lane == leader) base = atomicAdd(&cursors[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (sd == 0) return;
+    uint32_t pos = offsets[key] + base + (uint32_t)__popc(peers & ((1u << lane) - 1));
     size_t pidx = (use_table ? (size_t)w * table_stride : 0) + base_off + i;
     entries[pos] = (uint32_t)pidx | (sd < 0 ? 0x80000000u : 0u);
 }
@@ -270,24 +278,41 @@ __global__ void __launch_bounds__(128) k_bucket_finish(const uint32_t* __restric
 constexpr unsigned TREE_THREADS = 256;              // 64 quads per CTA in the reduction kernels
 constexpr unsigned TREE_QUADS = TREE_THREADS / 4;
 
-// One CTA per giant bucket: its quads stride over the partial list, then the block tree (quad.cuh).
+// GIANT_SLICES CTAs per giant bucket: each sums a contiguous slice of the bucket's partial list (quads stride over it, then
+// the block tree, quad.cuh); the last CTA to arrive (ticket counter) adds the slice sums and writes the bucket.
+constexpr unsigned GIANT_SLICES = 16;
 template <class F>
 __global__ void __launch_bounds__(TREE_THREADS) k_giant_finish(const uint32_t* __restrict__ giants, const uint32_t* __restrict__ meta,
                                                                const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t K,
-                                                               xyzz_t* buckets, const xyzz_t* __restrict__ partials) {
+                                                               xyzz_t* buckets, const xyzz_t* __restrict__ partials, xyzz_t* slice_sums,
+                                                               uint32_t* tickets) {
     extern __shared__ xyzz_t sm_tree[];
+    __shared__ uint32_t ticket_s;
     const uint32_t ng = meta[2];
     if (ng > MSM_MAX_GIANTS || blockIdx.x >= ng) return;  // overflow: k_bucket_finish took them
     const uint32_t b = giants[blockIdx.x];
     const uint32_t nbk = offsets[b + 1] - offsets[b], sb = (nbk + K - 1) / K, t0 = task_off[b];
+    const uint32_t per = (sb + GIANT_SLICES - 1) / GIANT_SLICES;
+    const uint32_t j_lo = blockIdx.y * per, j_hi = min(sb, j_lo + per);
     const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
     xyzz_t acc = xyzz_identity();
-    for (uint32_t j0 = 0; j0 < sb; j0 += nq) {
-        xyzz_t o = j0 + qd < sb ? load_xyzz(partials + t0 + j0 + qd) : xyzz_identity();
+    for (uint32_t j0 = j_lo; j0 < j_hi; j0 += nq) {
+        xyzz_t o = j0 + qd < j_hi ? load_xyzz(partials + t0 + j0 + qd) : xyzz_identity();
         acc = xyzz_add_quad<F>(acc, o);
     }
     acc = block_tree_sum_quad<F>(acc, sm_tree);
-    if (threadIdx.x == 0) store_xyzz(buckets + b, acc);
+    xyzz_t* mine = slice_sums + (size_t)blockIdx.x * GIANT_SLICES;
+    if (threadIdx.x == 0) {
+        store_xyzz(mine + blockIdx.y, acc);
+        __threadfence();
+        ticket_s = atomicAdd(&tickets[blockIdx.x], 1u);
+    }
+    __syncthreads();
+    if (ticket_s != GIANT_SLICES - 1) return;
+    __threadfence();
+    acc = qd < GIANT_SLICES ? load_xyzz(mine + qd) : xyzz_identity();
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
+    if (threadIdx.x == 0) { store_xyzz(buckets + b, acc); tickets[blockIdx.x] = 0; }
 }
 
 // sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of i = b+1 set, i in [1, B], B = 2^(c-1).
@@ -343,7 +368,7 @@ static void free_dev(void* p) { if (p) cudaFree(p); }
 void msm_workspace_free(MsmWorkspace& ws) {
     free_dev(ws.d_digits); free_dev(ws.d_entries); free_dev(ws.d_partials);
     free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_buckets);
-    free_dev(ws.d_bitsums); free_dev(ws.d_meta); free_dev(ws.d_giants);
+    free_dev(ws.d_bitsums); free_dev(ws.d_meta); free_dev(ws.d_giants); free_dev(ws.d_giant_slices); free_dev(ws.d_giant_tickets);
     if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
     for (auto& e : ws.ev) if (e) cudaEventDestroy(e);
     ws = MsmWorkspace();
@@ -442,6 +467,9 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
         if (!ws.d_meta) {
             ZK_CUDA(cudaMalloc(&ws.d_meta, 4 * sizeof(uint32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_giants, MSM_MAX_GIANTS * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_giant_slices, (size_t)MSM_MAX_GIANTS * GIANT_SLICES * sizeof(xyzz_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_giant_tickets, MSM_MAX_GIANTS * sizeof(uint32_t)));
+            ZK_CUDA(cudaMemsetAsync(ws.d_giant_tickets, 0, MSM_MAX_GIANTS * sizeof(uint32_t), st));
         }
     }
     unsigned nl = 0;
@@ -472,7 +500,8 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     else
         k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
                                                                                   ws.d_buckets, ws.d_partials);
-    k_giant_finish<F><<<MSM_MAX_GIANTS, TREE_THREADS, TREE_QUADS * sizeof(xyzz_t), st>>>(ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials);
+    k_giant_finish<F><<<dim3(MSM_MAX_GIANTS, GIANT_SLICES), TREE_THREADS, TREE_QUADS * sizeof(xyzz_t), st>>>(
+        ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials, ws.d_giant_slices, ws.d_giant_tickets);
     STAGE_MARK(5);
     // 6. bit-sliced bucket sums
     xyzz_t* d_partial = ws.d_bitsums;

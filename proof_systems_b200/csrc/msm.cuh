@@ -52,6 +52,8 @@ struct MsmWorkspace {
     xyzz_t* h_bitsums = nullptr;      // pinned host copy of [G][c]
     uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets
     uint32_t* d_giants = nullptr;     // [MSM_MAX_GIANTS] bucket ids
+    xyzz_t* d_giant_slices = nullptr; // [MSM_MAX_GIANTS][GIANT_SLICES] per-CTA slice sums of a giant's partials
+    uint32_t* d_giant_tickets = nullptr;  // [MSM_MAX_GIANTS] arrival counters (self-resetting)
     uint32_t chunk = 0;               // K override (0: chosen per call so that the tasks fill whole waves)
     int sm_count = 148;               // SMs of the device (set by the context)
     bool profile = false;             // record an event after every stage

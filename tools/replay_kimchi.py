@@ -46,6 +46,13 @@ def inputs():
     return g, lag, wit_m, dense, big
 
 
+def pinned(a):
+    """copy of `a` in page-locked host memory (what a production caller would hand to the library)"""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).pin_memory()
+    return t.numpy().view(np.uint64)
+
+
 def run_gpu(g, lag, wit_m, dense, big):
     ctx = zk.Context(0)
     t_setup = time.perf_counter()
@@ -61,17 +68,21 @@ def run_gpu(g, lag, wit_m, dense, big):
         out[name] = time.perf_counter() - t0
         return r
 
+    # working buffers in pinned host memory; transforms run in place on them (a Rust caller transforms its own Vec)
+    p_wit, p_dense, p_big = pinned(wit_m), pinned(dense), pinned(big)
+    p_pad = pinned(np.zeros((16, 8 * N, 4), dtype=np.uint64))
+    p_wit2, p_big4 = pinned(wit_m), pinned(big[: 4 * N])
+
     def once():
-        stage("15 witness commitments", lambda: [srs.commit_evaluations_non_hiding(N, wit_m[k]) for k in range(15)])
-        stage("15 iFFT(n)", lambda: ctx.ntt(FS, wit_m, inverse=True))
-        stage("z: iFFT(n) + MSM", lambda: (ctx.ntt(FS, dense[0], inverse=True), srs.commit_non_hiding(dense[0], 1)))
-        pad = np.zeros((16, 8 * N, 4), dtype=np.uint64)
-        pad[:15, :N] = wit_m
-        pad[15, :N] = dense[0]
-        stage("16 FFT(8n)", lambda: ctx.ntt(FS, pad, in_len=N))
-        stage("iFFT(4n) + iFFT(8n)", lambda: (ctx.ntt(FS, big[: 4 * N], inverse=True), ctx.ntt(FS, big, inverse=True)))
-        stage("t: 7 MSMs", lambda: srs.commit_non_hiding(dense[1:].reshape(-1, 4), 7))
-        stage("2 iFFT(n)", lambda: ctx.ntt(FS, dense[:2], inverse=True))
+        stage("15 witness commitments", lambda: [srs.commit_evaluations_non_hiding(N, p_wit[k]) for k in range(15)])
+        stage("15 iFFT(n)", lambda: ctx.ntt_inplace(FS, p_wit2, inverse=True))
+        stage("z: iFFT(n) + MSM", lambda: (ctx.ntt_inplace(FS, p_dense[0], inverse=True), srs.commit_non_hiding(p_dense[0], 1)))
+        p_pad[:15, :N] = p_wit
+        p_pad[15, :N] = p_dense[0]
+        stage("16 FFT(8n)", lambda: ctx.ntt_inplace(FS, p_pad, in_len=N))
+        stage("iFFT(4n) + iFFT(8n)", lambda: (ctx.ntt_inplace(FS, p_big4, inverse=True), ctx.ntt_inplace(FS, p_big, inverse=True)))
+        stage("t: 7 MSMs", lambda: srs.commit_non_hiding(p_dense[1:].reshape(-1, 4), 7))
+        stage("2 iFFT(n)", lambda: ctx.ntt_inplace(FS, p_dense[:2], inverse=True))
 
         def open_rounds():
             res = []
