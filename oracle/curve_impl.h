@@ -183,9 +183,15 @@ static inline size_t CN(ceil_log2)(size_t x) {
  * (Algorithm recalled from the published crate — SURVEY.md Appendix C; only the resulting group element
  * is pinned by the reference's vectors.)  Lengths: uses min(len(bases), len(scalars)) like msm_bigint.
  */
-static void CN(msm_pippenger)(CN(jac) *r, const CN(aff) *bases, const uint64_t *scalars, size_t n, int threads) {
+static void CN(msm_pippenger_parts)(CN(jac) *r, const CN(aff) *bases, const uint64_t *scalars, size_t n, unsigned parts, int threads) {
+    /* parts = 1: one msm_bigint call.  parts = 2: the reference's rayon::join of two half-size calls followed by one
+     * addition (poly-commitment/src/ipa.rs:652-662).  All (part, window) pairs form ONE flat task list — what rayon's
+     * work stealing makes of the nested parallelism — so no nested OpenMP teams are created. */
     if (n == 0) { CN(jac_set_inf)(r); return; }
-    unsigned c = n < 32 ? 3 : (unsigned)(CN(ceil_log2)(n) * 69 / 100 + 2);
+    if (parts < 1) parts = 1;
+    if (parts > n) parts = (unsigned)n;
+    size_t pn_max = (n + parts - 1) / parts;
+    unsigned c = pn_max < 32 ? 3 : (unsigned)(CN(ceil_log2)(pn_max) * 69 / 100 + 2);   /* ark: ln_without_floats(size) + 2 */
     const unsigned num_bits = 255;
     unsigned nwin = (num_bits + c - 1) / c;
     int32_t *digits = (int32_t *)malloc((size_t)n * nwin * sizeof(int32_t));
@@ -205,16 +211,20 @@ static void CN(msm_pippenger)(CN(jac) *r, const CN(aff) *bases, const uint64_t *
             digits[i * nwin + w] = (int32_t)d;
         }
     }
-    CN(jac) *wsum = (CN(jac) *)malloc(nwin * sizeof(CN(jac)));
+    CN(jac) *wsum = (CN(jac) *)malloc((size_t)parts * nwin * sizeof(CN(jac)));
     size_t nb = (size_t)1 << (c - 1);
     /* the last window can hold an un-recoded digit up to 2^c */
     size_t nb_last = (size_t)1 << c;
-#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
-    for (unsigned w = 0; w < nwin; w++) {
+    int tasks = (int)(parts * nwin);
+    int thr = threads < tasks ? threads : tasks;
+#pragma omp parallel for num_threads(thr) schedule(dynamic, 1)
+    for (int t = 0; t < tasks; t++) {
+        unsigned p = (unsigned)t / nwin, w = (unsigned)t % nwin;
+        size_t lo = n * p / parts, hi = n * (p + 1) / parts;
         size_t nbw = (w == nwin - 1) ? nb_last : nb;
         CN(jac) *bk = (CN(jac) *)malloc(nbw * sizeof(CN(jac)));
         for (size_t b = 0; b < nbw; b++) CN(jac_set_inf)(&bk[b]);
-        for (size_t i = 0; i < n; i++) {
+        for (size_t i = lo; i < hi; i++) {
             int32_t d = digits[i * nwin + w];
             if (d > 0) CN(jac_add_mixed)(&bk[d - 1], &bk[d - 1], &bases[i]);
             else if (d < 0) { CN(aff) nq; CN(aff_neg)(&nq, &bases[i]); CN(jac_add_mixed)(&bk[-d - 1], &bk[-d - 1], &nq); }
@@ -224,17 +234,25 @@ static void CN(msm_pippenger)(CN(jac) *r, const CN(aff) *bases, const uint64_t *
             CN(jac_add)(&run, &run, &bk[b]);
             CN(jac_add)(&tot, &tot, &run);
         }
-        wsum[w] = tot;
+        wsum[t] = tot;
         free(bk);
     }
-    CN(jac) acc = wsum[nwin - 1];
-    for (int w = (int)nwin - 2; w >= 0; w--) {
-        for (unsigned k = 0; k < c; k++) CN(jac_double)(&acc, &acc);
-        CN(jac_add)(&acc, &acc, &wsum[w]);
+    CN(jac) total; CN(jac_set_inf)(&total);
+    for (unsigned p = 0; p < parts; p++) {
+        CN(jac) acc = wsum[p * nwin + nwin - 1];
+        for (int w = (int)nwin - 2; w >= 0; w--) {
+            for (unsigned k = 0; k < c; k++) CN(jac_double)(&acc, &acc);
+            CN(jac_add)(&acc, &acc, &wsum[p * nwin + w]);
+        }
+        CN(jac_add)(&total, &total, &acc);
     }
-    *r = acc;
+    *r = total;
     free(wsum);
     free(digits);
+}
+
+static void CN(msm_pippenger)(CN(jac) *r, const CN(aff) *bases, const uint64_t *scalars, size_t n, int threads) {
+    CN(msm_pippenger_parts)(r, bases, scalars, n, 1, threads);
 }
 
 /*

@@ -85,8 +85,6 @@ static int default_threads(int t) {
 EXPORT int orc_max_threads(void) { return default_threads(0); }
 
 /* ---- field API ---- */
-#define FIELD_DISPATCH2(fid, fn, ...) do { if ((fid) == 0) fp_##fn(__VA_ARGS__); else fq_##fn(__VA_ARGS__); } while (0)
-
 EXPORT void orc_fe_modulus(int fid, uint64_t out[4]) { memcpy(out, fid == 0 ? fp_MOD : fq_MOD, 32); }
 EXPORT void orc_fe_mul(int fid, const uint64_t *a, const uint64_t *b, uint64_t *r) {
     if (fid == 0) fp_mul((fp_t *)r, (const fp_t *)a, (const fp_t *)b);
@@ -218,24 +216,16 @@ EXPORT void orc_msm(int cid, const uint64_t *bases, const uint64_t *scalars, siz
 
 /* The reference's commit_non_hiding for a polynomial of exactly |g| coefficients (poly-commitment/src/ipa.rs:652-662):
  * rayon::join of two half-size MSMs, then one addition — the "vertical" split benchmarked in benches/msm.rs:71-88.
- * Each half gets half of the threads (windows in parallel inside, like rayon's nested work-stealing). */
+ * The 2 x windows tasks run as one flat list (rayon's work stealing), see msm_pippenger_parts. */
 EXPORT void orc_msm_split2(int cid, const uint64_t *bases, const uint64_t *scalars, size_t n, int threads, uint64_t *out_aff) {
     threads = default_threads(threads);
-    int th = threads / 2 > 0 ? threads / 2 : 1;
-    size_t h = n / 2;
-    uint64_t j0[12], j1[12], sum[12];
-#ifdef _OPENMP
-    omp_set_max_active_levels(2);
-#endif
-#pragma omp parallel sections num_threads(2)
-    {
-#pragma omp section
-        orc_msm(cid, bases, scalars, h, 0, th, j0, NULL);
-#pragma omp section
-        orc_msm(cid, bases + 8 * h, scalars + 4 * h, n - h, 0, th, j1, NULL);
+    if (cid == 0) {
+        pallas_jac r; pallas_msm_pippenger_parts(&r, (const pallas_aff *)bases, scalars, n, 2, threads);
+        pallas_jac_to_aff((pallas_aff *)out_aff, &r);
+    } else {
+        vesta_jac r; vesta_msm_pippenger_parts(&r, (const vesta_aff *)bases, scalars, n, 2, threads);
+        vesta_jac_to_aff((vesta_aff *)out_aff, &r);
     }
-    orc_jac_add(cid, j0, j1, sum);
-    orc_jac_to_affine(cid, sum, out_aff);
 }
 
 /* == G::Group::msm(bases, scalars): scalars in Montgomery form (into_bigint first, like

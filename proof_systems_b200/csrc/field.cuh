@@ -97,10 +97,6 @@ struct FqParams {  // curves/src/pasta/fields/fq.rs:29-48
 };
 constexpr uint32_t M7 = 0x40000000u;  // both fields: bit 254
 
-template <class F> ZK_HD constexpr uint32_t mod_limb(int i) {
-    return i == 0 ? 1u : i == 1 ? F::M1 : i == 2 ? F::M2 : i == 3 ? F::M3 : i == 7 ? M7 : 0u;
-}
-
 struct alignas(16) fe {
     uint32_t v[8];
 };

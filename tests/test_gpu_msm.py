@@ -166,3 +166,65 @@ def test_config4_2_20_vesta_sharded(ctx, orc, vesta_srs):
             parts.append(ctx.msm(bases, sc[lo:hi], off=lo))
         assert np.array_equal(zk.jacobian_to_affine(srs.cid, zk.jacobian_sum(srs.cid, np.stack(parts))), want), world
     bases.free()
+
+
+def test_pinned_scalars_zero_copy(ctx, orc, pallas_srs):
+    import torch
+    srs = pallas_srs
+    n = 3000
+    sc = orc.random_scalars(srs.scalar, n, seed=13)
+    pinned = torch.from_numpy(sc.view(np.int64).copy()).pin_memory().numpy().view(np.uint64)
+    bases = ctx.upload_bases(srs.cid, srs.g[:n], window_bits=-1)
+    assert np.array_equal(ctx.msm_affine(bases, pinned), orc.msm(srs.cid, srs.g[:n], sc))
+    bases.free()
+
+
+def test_concurrent_callers_share_one_context(ctx, orc, vesta_srs):
+    """kimchi commits its 15 witness columns from 15 rayon workers against one Arc<SRS> (kimchi/src/prover.rs:329-351;
+    SRS: Sync + Send, poly-commitment/src/lib.rs:61): the C ABI must be re-entrant.  Eight Python threads (ctypes
+    releases the GIL during the call) hammer one context with different scalar vectors."""
+    import threading
+    srs = vesta_srs
+    n = 1024
+    bases = ctx.upload_bases(srs.cid, srs.g[:n], window_bits=-1)
+    scs = [orc.random_scalars(srs.scalar, n, seed=100 + t) for t in range(8)]
+    want = [orc.msm(srs.cid, srs.g[:n], s) for s in scs]
+    got, errs = [None] * 8, []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                got[t] = ctx.msm_affine(bases, scs[t])
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for t in range(8):
+        assert np.array_equal(got[t], want[t]), t
+    bases.free()
+
+
+def test_error_codes(ctx, orc, pallas_srs):
+    """invalid arguments come back as error codes with a message, never as a crash"""
+    srs = pallas_srs
+    bases = ctx.upload_bases(srs.cid, srs.g[:64], window_bits=0)
+    sc = orc.random_scalars(srs.scalar, 64, seed=1)
+    with pytest.raises(zk.ZkError) as e:
+        ctx.msm(bases, sc, off=10)                     # slice [10, 74) outside the 64 resident bases
+    assert e.value.code == -1 and "outside" in str(e.value)
+    with pytest.raises(zk.ZkError):
+        ctx.msm(bases, sc, window_bits=17)
+    with pytest.raises(zk.ZkError):
+        ctx.upload_bases(7, srs.g[:4])                 # unknown curve id
+    with pytest.raises(zk.ZkError):
+        ctx.ntt(5, np.zeros((4, 4), dtype=np.uint64))  # unknown field id
+    with pytest.raises(zk.ZkError):
+        ctx.ntt_dev(zk.FP, 0, 21)                      # log_n beyond the two-pass plan
+    other = zk.Context(0)
+    with pytest.raises(zk.ZkError):
+        other.msm(bases, sc)                           # bases belong to another context
+    other.close()
+    bases.free()

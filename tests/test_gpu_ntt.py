@@ -101,3 +101,16 @@ def test_domain_chain_d1_in_d8(ctx, orc):
     big[:n] = c
     ev8 = ctx.ntt(fid, big, in_len=n)
     assert np.array_equal(ev8[::8], ctx.ntt(fid, c))
+
+
+def test_pinned_host_memory_is_transformed_in_place(ctx, orc):
+    """zero-copy path of zk_ntt_batch / zk_msm: page-locked buffers are read and written over PCIe by the kernels"""
+    import torch
+    for log_n, batch in ((9, 3), (14, 2)):
+        n = 1 << log_n
+        a = orc.to_mont(zk.FQ, orc.random_scalars(zk.FQ, n * batch, seed=77)).reshape(batch, n, 4)
+        t = torch.from_numpy(a.view(np.int64).copy()).pin_memory()
+        view = t.numpy().view(np.uint64)
+        ctx.ntt_inplace(zk.FQ, view, inverse=True)
+        for j in range(batch):
+            assert np.array_equal(view[j], orc.ntt(zk.FQ, a[j], inverse=True)), (log_n, j)
