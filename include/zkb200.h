@@ -77,6 +77,11 @@ void zk_bases_free(zk_bases* bases);
 size_t zk_bases_len(const zk_bases* bases);
 int zk_bases_window_bits(const zk_bases* bases);
 
+/* Point decompression on the device: n points in ark-serialize's compressed short-Weierstrass form — the format of
+ * srs/pallas.srs / srs/vesta.srs through SerdeAs (utils/src/serialization.rs:65-106): 32-byte LE canonical x, then a flag
+ * byte (bit 7: y is the larger root, bit 6: infinity) — to affine Montgomery points.  ZK_ERR_INVALID if some x is off-curve. */
+int zk_points_decompress(zk_ctx* ctx, int curve_id, const uint8_t* in33, size_t n, uint64_t* out_xy);
+
 /* ------------------------------------------------------------------ MSM
  * zk_msm == <G::Group as VariableBaseMSM>::msm_bigint(&bases[off..off+n], scalars)   (scalars_are_mont = 0: canonical
  *           integers, poly-commitment/src/ipa.rs:672,943,953; commitment.rs:382,387)

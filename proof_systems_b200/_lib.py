@@ -57,6 +57,7 @@ def lib() -> ctypes.CDLL:
     L.zk_bases_len.argtypes = [vp]
     L.zk_bases_len.restype = sz
     L.zk_bases_window_bits.argtypes = [vp]
+    L.zk_points_decompress.argtypes = [vp, i, vp, sz, _u64p]
     L.zk_msm.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
     L.zk_msm_dev.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
     L.zk_msm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i, i, _u64p]
@@ -155,6 +156,14 @@ class Context:
         check(lib().zk_ctx_last_stage_ms(self._h, buf, 8))
         names = ["recode", "plan", "scatter", "accumulate", "finish", "bitsum", "ntt"]
         return {k: float(buf[i]) for i, k in enumerate(names)}
+
+    def decompress_points(self, curve: int, raw33) -> np.ndarray:
+        """ark-serialize compressed points (bytes or uint8 [n, 33], the srs/*.srs form) -> affine Montgomery [n, 8]"""
+        buf = np.frombuffer(raw33, dtype=np.uint8) if isinstance(raw33, (bytes, bytearray)) else np.ascontiguousarray(raw33, dtype=np.uint8).reshape(-1)
+        n = buf.size // 33
+        out = np.empty((n, 8), dtype=np.uint64)
+        check(lib().zk_points_decompress(self._h, curve, ctypes.c_void_p(buf.ctypes.data), n, out.ctypes.data_as(_u64p)))
+        return out
 
     # ------------------------------------------------------------------ MSM
     def upload_bases(self, curve: int, points, window_bits: int = -1) -> "Bases":

@@ -14,6 +14,8 @@
 
 namespace zkb {
 
+template <class F> int points_decompress(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st);   // decompress.cu
+
 static thread_local char g_err[512] = "";
 void zk_set_error(const char* fmt, ...) {
     va_list ap;
@@ -301,6 +303,35 @@ void zk_bases_free(zk_bases* bases) {
 
 size_t zk_bases_len(const zk_bases* bases) { return bases ? bases->b.n : 0; }
 int zk_bases_window_bits(const zk_bases* bases) { return bases ? (int)bases->b.c : 0; }
+
+// ark-serialize compressed points (33 bytes each) -> affine Montgomery points; host pointers
+int zk_points_decompress(zk_ctx* ctx, int curve_id, const uint8_t* in33, size_t n, uint64_t* out_xy) {
+    if (!ctx || (!in33 && n) || (!out_xy && n)) { zk_set_error("points_decompress: null argument"); return ZK_ERR_INVALID; }
+    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("points_decompress: unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return ZK_OK;
+    uint8_t* d_in = nullptr;
+    affine_t* d_out = nullptr;
+    unsigned* d_bad = nullptr;
+    unsigned bad = 0;
+    ZK_CUDA(cudaMalloc(&d_in, 33 * n));
+    ZK_CUDA(cudaMalloc(&d_out, n * sizeof(affine_t)));
+    ZK_CUDA(cudaMalloc(&d_bad, sizeof(unsigned)));
+    ZK_CUDA(cudaMemcpyAsync(d_in, in33, 33 * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = curve_id == ZK_PALLAS ? points_decompress<FpParams>(d_in, d_out, n, d_bad, ctx->stream)
+                                   : points_decompress<FqParams>(d_in, d_out, n, d_bad, ctx->stream);
+    if (rc == ZK_OK) {
+        ctx->launches += 1;
+        cudaMemcpyAsync(out_xy, d_out, n * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(&bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { zk_set_error("points_decompress: %s", cudaGetErrorString(e)); rc = ZK_ERR_CUDA; }
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_bad);
+    if (rc == ZK_OK && bad) { zk_set_error("points_decompress: %u of %zu x-coordinates are not on the curve", bad, n); return ZK_ERR_INVALID; }
+    return rc;
+}
 
 // ---------------------------------------------------------------------------------------------- MSM
 int zk_msm_dev(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* d_scalars, int scalars_are_mont, int window_bits, uint64_t out_xyz[12]) {

@@ -93,3 +93,29 @@ def test_mask_custom(ctx, orc, vesta_srs):
     with pytest.raises(BlindersDontMatch):
         srs.mask_custom(com, blinders[:1])
     srs.close()
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_device_point_decompression(ctx, orc, request, name):
+    """srs/{pallas,vesta}.srs store compressed generators (utils/src/serialization.rs:65-106); the device decoder must
+    reproduce the uncompressed coordinates of srs/test_*.srs and agree with the oracle on every point, incl. infinity."""
+    g = request.getfixturevalue(name)
+    got = ctx.decompress_points(g.cid, g.g_cmp)
+    assert np.array_equal(got[:2048], g.mont_points(g.g_xy_canon))
+    assert np.array_equal(got, g.g)                       # oracle decompression of the whole fixture
+    inf = bytes(32) + bytes([0x40])
+    mixed = g.g_cmp[:3].tobytes() + inf + g.g_cmp[3:5].tobytes()
+    out = ctx.decompress_points(g.cid, mixed)
+    assert not np.any(out[3]) and np.array_equal(out[4], g.g[3])
+    # flipping the sign flag gives the negated point; an x that is off the curve is rejected
+    flipped = bytearray(g.g_cmp[0].tobytes()); flipped[32] ^= 0x80
+    neg = ctx.decompress_points(g.cid, bytes(flipped))[0]
+    assert np.array_equal(neg[:4], g.g[0][:4]) and not np.any(orc.affine_add(g.cid, neg, g.g[0]))
+    bad = None
+    for x in range(2, 40):   # find a small x with x^3 + 5 a non-residue
+        if orc.fe_sqrt(g.base, orc.fe_add(g.base, orc.fe_mul(g.base, orc.fe_mul(g.base, orc.fe(g.base, x), orc.fe(g.base, x)), orc.fe(g.base, x)), orc.fe(g.base, 5))) is None:
+            bad = x.to_bytes(32, "little") + bytes([0])
+            break
+    assert bad is not None
+    with pytest.raises(zk.ZkError):
+        ctx.decompress_points(g.cid, bad)
