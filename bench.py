@@ -84,12 +84,31 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def make_inputs(orc, rank):
-    """Pallas SRS generators (the reference's own srs/pallas.srs, via tests/golden) + seeded scalars / polynomial."""
-    z = np.load(os.path.join(ROOT, "tests", "golden", "pallas_srs.npz"))
-    g = orc.decompress(orc.PALLAS, z["g_cmp"].tobytes())           # input preparation only
-    scalars = orc.random_scalars(orc.FQ, N_PTS, seed=1 + rank)     # canonical (msm_bigint form)
-    poly = orc.to_mont(orc.FP, orc.random_scalars(orc.FP, N_PTS, seed=2))
+def splitmix64_limbs(seed, n):
+    """n synthetic field elements: 4 splitmix64 words each, top limb masked to 62 bits (uniform below 2^254 < m).
+    Used as canonical MSM scalars and, read as Montgomery residues, as NTT input (every value < m is a valid residue)."""
+    idx = np.arange(1, 4 * n + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    w = z.reshape(n, 4).copy()
+    w[:, 3] &= np.uint64((1 << 62) - 1)
+    return w
+
+
+def compressed_srs():
+    """the reference's own srs/pallas.srs generators (compressed, 33 B each), via tests/golden"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "pallas_srs.npz"))["g_cmp"]
+
+
+def make_inputs(decompress, rank):
+    """Pallas SRS generators + seeded scalars / polynomial.  `decompress`: the product's device decoder (our arm) or the
+    oracle's (reference arm)."""
+    g = decompress(compressed_srs())
+    scalars = splitmix64_limbs(1 + rank, N_PTS)      # canonical (msm_bigint form)
+    poly = splitmix64_limbs(2, N_PTS)                # Montgomery residues
     return g, scalars, poly
 
 
@@ -116,7 +135,7 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     threads = orc.host_threads()
-    g, scalars, poly = make_inputs(orc, 0)
+    g, scalars, poly = make_inputs(lambda c: orc.decompress(orc.PALLAS, c.tobytes()), 0)
     for _ in range(max(1, args.warmup)):
         cpu_msm(orc, g, scalars, threads)
     t0 = time.perf_counter()
@@ -171,10 +190,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from oracle import oracle as orc   # input preparation + the cpu_baseline leg + the correctness check of the timed result
-
-    g, scalars, poly = make_inputs(orc, rank)
     ctx = zk.Context(local)
+    g, scalars, poly = make_inputs(lambda c: ctx.decompress_points(zk.PALLAS, c), rank)   # inputs come from the product itself
     stream = torch.cuda.Stream(device=local)
     ctx.set_stream(stream.cuda_stream)
     bases = ctx.upload_bases(zk.PALLAS, g, window_bits=args.window_bits)
@@ -292,7 +309,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- correctness of what was timed + CPU baseline on the same host (bounded sample)
+    # ---- correctness of what was timed + CPU baseline on the same host (bounded sample): the only use of the oracle
+    from oracle import oracle as orc
     threads = orc.host_threads()
     if world == 1:
         want = orc.msm(orc.PALLAS, g, scalars)
@@ -300,7 +318,7 @@ def main():
         tot = [0] * N_PTS
         m = orc.FQ_MODULUS
         for r in range(world):
-            sr = orc.limbs_to_ints(orc.random_scalars(orc.FQ, N_PTS, seed=1 + r))
+            sr = orc.limbs_to_ints(splitmix64_limbs(1 + r, N_PTS))
             tot = [(a + b) % m for a, b in zip(tot, sr)]
         want = orc.msm(orc.PALLAS, g, orc.ints_to_limbs(tot))
     ok = bool(np.array_equal(zk.jacobian_to_affine(zk.PALLAS, result), want))
