@@ -127,6 +127,20 @@ def cpu_msm(orc, g, scalars, threads):
     return orc.msm_split2(orc.PALLAS, g, scalars, threads=threads)
 
 
+def best_threads(fn, max_threads):
+    """The GPU boxes expose 64-128 hardware threads that are not always all usable (shared host, cgroup quota): run the CPU
+    arm once per candidate thread count and keep the fastest — the baseline gets its best configuration."""
+    best, best_t = None, None
+    cand = sorted({t for t in (8, 16, 32, 64, 128, max_threads) if t <= max_threads} or {max_threads})
+    for t in cand:
+        t0 = time.perf_counter()
+        fn(t)
+        el = time.perf_counter() - t0
+        if best is None or el < best:
+            best, best_t = el, t
+    return best_t
+
+
 def run_reference(args):
     """The reference's CPU path for this workload, as restated by the oracle (oracle/pasta_oracle.c: ark-style signed-digit
     Pippenger with window-parallel threads; ark-style radix-2 FFT), all host threads."""
@@ -134,8 +148,8 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as orc
-    threads = orc.host_threads()
     g, scalars, poly = make_inputs(lambda c: orc.decompress(orc.PALLAS, c.tobytes()), 0)
+    threads = best_threads(lambda t: cpu_msm(orc, g, scalars, t), orc.host_threads())
     for _ in range(max(1, args.warmup)):
         cpu_msm(orc, g, scalars, threads)
     t0 = time.perf_counter()
@@ -154,7 +168,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "u256 (4 x u64 Montgomery limbs)", "data": "synthetic",
         "config": {"workload": "2^16-point Pallas MSM on srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)",
                    "cpu_path": "oracle port of ark-ec 0.5 msm_bigint under the reference's 2-way rayon::join split (ipa.rs:652-662); the reference is Rust and there is no cargo in the image"},
-        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample, "host_threads_available": orc.host_threads()},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ntt": {"metric": "fp_ntt_elements_per_s", "value": N_PTS / ntt_s, "unit": "elements/s", "ms": ntt_s * 1e3,
                 "workload": "2^16-element Fp forward NTT", "cores": threads},
@@ -311,7 +325,7 @@ def main():
 
     # ---- correctness of what was timed + CPU baseline on the same host (bounded sample): the only use of the oracle
     from oracle import oracle as orc
-    threads = orc.host_threads()
+    threads = best_threads(lambda t: cpu_msm(orc, g, scalars, t), orc.host_threads())
     if world == 1:
         want = orc.msm(orc.PALLAS, g, scalars)
     else:
@@ -358,7 +372,7 @@ def main():
                              "the accumulation kernel gathers 64 B per (point, window) from the resident table, which is what `traffic` shows",
                      "stage_ms": stages},
         "cpu_baseline": {"value": N_PTS / cpu_msm_s, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"{cpu_reps} x the same 2^16-point MSM (oracle: ark-style Pippenger, 2-way split, {threads} threads), {cpu_msm_s * 1e3:.1f} ms each"},
+                         "sample": f"{cpu_reps} x the same 2^16-point MSM (oracle: ark-style Pippenger, 2-way split, best of 8..{orc.host_threads()} threads = {threads}), {cpu_msm_s * 1e3:.1f} ms each"},
         "ntt": {
             "metric": "fp_ntt_elements_per_s", "workload": "2^16-element Fp forward NTT (Radix2EvaluationDomain::fft_in_place)" + ("" if world == 1 else f", {world} replicas"),
             "value": world * N_PTS / (ntt_ms / args.steps * 1e-3), "unit": "elements/s", "ms_per_step": ntt_ms / args.steps,
