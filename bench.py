@@ -222,11 +222,10 @@ def main():
     def flush_l2():
         flush.fill_(rank + 1)
 
-    from proof_systems_b200.parallel import all_gather_point_sum
+    from proof_systems_b200.parallel import PointSumAllGather
 
-    def reduce_partials(jac):
-        """final point-sum: one NCCL all_gather of the 96-byte Jacobian partials, then N-1 additions"""
-        return all_gather_point_sum(zk.PALLAS, jac, device=torch.device("cuda", local))
+    # final point-sum: one NCCL all_gather of the 96-byte Jacobian partials, then N-1 additions on every rank
+    reduce_partials = PointSumAllGather(zk.PALLAS, torch.device("cuda", local))
 
     def step_resident():
         jac = ctx.msm_dev(bases, d_scalars.data_ptr(), N_PTS)
