@@ -404,7 +404,7 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     uint32_t K = ws.chunk;
     if (K == 0) {
         const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
-        size_t waves = (Mmax + 24 * capacity - 1) / (24 * capacity);
+        size_t waves = (Mmax + 64 * capacity - 1) / (64 * capacity);   // long tasks for large inputs: fewer partials to sum
         if (waves == 0) waves = 1;
         // a cheap finish pass affords twice as many (half as long, better balanced) tasks
         if (serial_finish && Mmax / (2 * waves * capacity) >= 6) waves *= 2;
