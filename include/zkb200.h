@@ -141,6 +141,26 @@ int zk_srs_commit_evaluations_non_hiding(zk_srs* srs, size_t domain_size, const 
 int zk_srs_mask_custom(zk_srs* srs, const uint64_t* chunks_xy, size_t n_chunks, const uint64_t* blinders_mont,
                        size_t n_blinders, uint64_t* out_xy);
 
+/* ------------------------------------------------------------------ IPA opening rounds, device resident (SRS::open, ipa.rs:929-1007)
+ * The coefficients a and the evaluation vector b are uploaded once and folded in HBM; the bases are the resident SRS table
+ * (`bases`, zk_bases_upload of srs.g) and are never folded: round j's commitments are MSMs over the original points with
+ * scalars a[.] * b_poly_coefficients(u_1..u_j)[.] (commitment.rs:565-581).  The host keeps the Fiat-Shamir sponge and the
+ * blinders.  Per round:
+ *   zk_ipa_round_lr    out_l = <a_hi, g_lo>, out_r = <a_lo, g_hi> (Jacobian; the host adds rand*h + ip*u_base, ipa.rs:943-961),
+ *                      out_ip_l = <a_hi, b_lo>, out_ip_r = <a_lo, b_hi> (Montgomery field elements)
+ *   zk_ipa_round_fold  a <- a_lo + u_inv a_hi,  b <- b_lo + u b_hi,  g <- g_lo + [u] g_hi (implicitly)  (ipa.rs:980-1006,
+ *                      u = u_pre.to_field(endo_r), Montgomery)
+ * n = the SRS size rounded up to a power of two (the reference pads g with the identity, a and b with zero, ipa.rs:848-862).
+ * zk_ipa_read copies the leading min(len, capacity) elements of the current a and b; after the last fold (len == 1) those are
+ * a0 and b0, and out_g_xyz (optional, Jacobian) receives g0, the proof's `sg`.  `bases` must outlive the handle. */
+typedef struct zk_ipa zk_ipa;
+int zk_ipa_begin(zk_ctx* ctx, const zk_bases* bases, const uint64_t* a_mont, const uint64_t* b_mont, size_t n, zk_ipa** out);
+void zk_ipa_free(zk_ipa* ipa);
+size_t zk_ipa_len(const zk_ipa* ipa);
+int zk_ipa_round_lr(zk_ipa* ipa, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12], uint64_t out_ip_l[4], uint64_t out_ip_r[4]);
+int zk_ipa_round_fold(zk_ipa* ipa, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]);
+int zk_ipa_read(zk_ipa* ipa, uint64_t* out_a, uint64_t* out_b, size_t capacity, uint64_t out_g_xyz[12]);
+
 /* ------------------------------------------------------------------ diagnostics (tests/test_gpu_field.py, DESIGN.md compute model)
  * Element-wise device field ops on n elements (op: 0 mul, 1 add, 2 sub, 3 inverse of a), host pointers. */
 int zk_debug_field_op(zk_ctx* ctx, int field_id, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

@@ -78,6 +78,14 @@ def lib() -> ctypes.CDLL:
     L.zk_srs_commit_non_hiding.argtypes = [vp, vp, sz, sz, _u64p, sz, ctypes.POINTER(sz)]
     L.zk_srs_commit_evaluations_non_hiding.argtypes = [vp, sz, vp, sz, _u64p]
     L.zk_srs_mask_custom.argtypes = [vp, vp, sz, vp, sz, _u64p]
+    L.zk_ipa_begin.argtypes = [vp, vp, vp, vp, sz, ctypes.POINTER(vp)]
+    L.zk_ipa_free.argtypes = [vp]
+    L.zk_ipa_free.restype = None
+    L.zk_ipa_len.argtypes = [vp]
+    L.zk_ipa_len.restype = sz
+    L.zk_ipa_round_lr.argtypes = [vp, _u64p, _u64p, _u64p, _u64p]
+    L.zk_ipa_round_fold.argtypes = [vp, _u64p, _u64p]
+    L.zk_ipa_read.argtypes = [vp, vp, vp, sz, _u64p]
     L.zk_debug_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.zk_debug_mul_throughput.argtypes = [vp, i, u, ctypes.POINTER(ctypes.c_double)]
     L.zk_debug_op_throughput.argtypes = [vp, i, i, u, u, u, ctypes.POINTER(ctypes.c_double)]

@@ -130,6 +130,20 @@ template <class F> ZK_HD xyzz_t xyzz_add(const xyzz_t& p, const xyzz_t& q) {
     return r;
 }
 
+// [k] P, k canonical (8 x u32), MSB first.  Leading zero bits are skipped; k = 0 gives the identity.
+template <class F> ZK_HD xyzz_t xyzz_scalar_mul(const xyzz_t& p, const fe& k) {
+    xyzz_t acc = xyzz_identity();
+    bool started = false;
+    for (int i = 255; i >= 0; i--) {
+        if (started) acc = xyzz_dbl<F>(acc);
+        if ((k.v[i >> 5] >> (i & 31)) & 1u) {
+            acc = started ? xyzz_add<F>(acc, p) : p;
+            started = true;
+        }
+    }
+    return acc;
+}
+
 // XYZZ -> affine with one field inversion: x = X / ZZ, y = Y / ZZZ.   1/ZZ = (ZZ*ZZZ)^-1 * ZZZ, 1/ZZZ = (..)^-1 * ZZ
 template <class F> ZK_HD affine_t xyzz_to_affine(const xyzz_t& p) {
     affine_t r;

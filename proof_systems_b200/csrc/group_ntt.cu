@@ -12,20 +12,6 @@
 
 namespace zkb {
 
-// [k] P, k canonical (8 x u32), MSB first.  Leading zero bits are skipped; k = 0 gives the identity.
-template <class F> __device__ xyzz_t xyzz_scalar_mul(const xyzz_t& p, const fe& k) {
-    xyzz_t acc = xyzz_identity();
-    bool started = false;
-    for (int i = 255; i >= 0; i--) {
-        if (started) acc = xyzz_dbl<F>(acc);
-        if ((k.v[i >> 5] >> (i & 31)) & 1u) {
-            acc = started ? xyzz_add<F>(acc, p) : p;
-            started = true;
-        }
-    }
-    return acc;
-}
-
 // tw[i] = w^{-i} as a CANONICAL integer, i < count (w = n-th root of unity of the scalar field); ninv[0] = n^-1 canonical
 template <class FS> __global__ void k_gntt_twiddles(fe* tw, fe* ninv, unsigned log_n, unsigned count) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;

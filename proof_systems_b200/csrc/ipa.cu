@@ -1,0 +1,233 @@
+// ipa.cu — device-resident state for the folding rounds of the IPA opening proof, SRS::open
+// (poly-commitment/src/ipa.rs:929-1007).  The coefficient vector a and the evaluation vector b are folded in HBM; the bases are
+// NEVER folded: after j rounds with challenges u_1..u_j the reference's folded bases are
+//     g_j[i] = sum_t s_j[t] * g[t * m_j + i],      m_j = n / 2^j,   s_j = b_poly_coefficients(u_1..u_j)  (commitment.rs:565-581)
+// so the round's two commitments are MSMs over the ORIGINAL, resident, table-precomputed SRS points with expanded scalars
+//     L_j = <a_hi, g_j,lo> = sum_{t, i < h} (a[h + i] s_j[t]) g[t m_j + i]          (h = m_j / 2; ipa.rs:943-961)
+//     R_j = <a_lo, g_j,hi> = sum_{t, i < h} (a[i] s_j[t])     g[t m_j + h + i]
+// and the final base g0 (the proof's `sg`) is <s_k, g>.  That replaces log2(n) rounds of per-point scalar multiplications
+// (G::combine_one_endo, commitment.rs:539 / combine.rs:292-342 — latency-bound chains of ~380 group operations per point) by
+// the throughput-bound MSM pipeline of msm.cu; the group elements produced are the same.  The host owns the Fiat-Shamir
+// sponge, rand_l / rand_r, h and u_base: it finishes L and R (two scalar multiplications), squeezes u, and asks for the fold
+//     a <- a_lo + u^-1 a_hi,   b <- b_lo + u b_hi,   s <- (s[t], u s[t])_t          (ipa.rs:980-1006)
+// SURVEY.md §8f row 1.
+#include <mutex>
+
+#include "../../include/zkb200.h"
+#include "ctx.hpp"
+#include "host_field.hpp"
+#include "msm.cuh"
+
+using namespace zkb;
+
+struct zk_ipa {
+    zk_ctx* ctx = nullptr;
+    int curve = 0;
+    size_t n = 0;           // current length (halves every fold)
+    size_t n0 = 0;          // original (padded) length
+    const zk_bases* bases = nullptr;
+    fe* d_s[2] = {nullptr, nullptr};   // b_poly_coefficients of the challenges so far (ping-pong), Montgomery
+    int cur = 0;
+    fe* d_sc = nullptr;     // expanded MSM scalars, n0 entries, Montgomery
+    fe* d_a = nullptr;
+    fe* d_b = nullptr;
+    fe* d_part = nullptr;   // inner-product partials
+    fe* h_ip = nullptr;     // pinned: two field elements
+};
+
+namespace zkb {
+
+constexpr unsigned IP_THREADS = 256, IP_BLOCKS = 64;
+
+// partial[blockIdx] = sum over the block's strided share of x[i] * y[i]  (Montgomery in, Montgomery out)
+template <class FS> __global__ void __launch_bounds__(IP_THREADS) k_inner_product(const fe* __restrict__ x, const fe* __restrict__ y, size_t m, fe* partial) {
+    __shared__ fe sm[IP_THREADS];
+    fe acc = fe_zero();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+        acc = fe_add<FS>(acc, fe_mul<FS>(load_fe_nc(x + i), load_fe_nc(y + i)));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned s = blockDim.x >> 1; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fe_add<FS>(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+template <class FS> __global__ void __launch_bounds__(IP_BLOCKS) k_inner_product_final(const fe* __restrict__ partial, fe* out) {
+    __shared__ fe sm[IP_BLOCKS];
+    sm[threadIdx.x] = partial[threadIdx.x];
+    __syncthreads();
+    for (unsigned s = IP_BLOCKS >> 1; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fe_add<FS>(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+
+// v[i] <- v[i] + c * v[i + half]
+template <class FS> __global__ void k_fold_field(fe* v, size_t half, fe c) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    store_fe(v + i, fe_add<FS>(load_fe(v + i), fe_mul<FS>(load_fe(v + i + half), c)));
+}
+
+// s_new[2t] = s[t], s_new[2t + 1] = u * s[t]
+template <class FS> __global__ void k_expand_challenges(const fe* __restrict__ s_old, fe* s_new, size_t count, fe u) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    fe v = load_fe_nc(s_old + t);
+    store_fe(s_new + 2 * t, v);
+    store_fe(s_new + 2 * t + 1, fe_mul<FS>(v, u));
+}
+
+// sc[t * m + i] = (right ? (i >= h ? a[i - h] : 0) : (i < h ? a[h + i] : 0)) * s[t],  m = 2h
+template <class FS> __global__ void k_expand_scalars(fe* sc, const fe* __restrict__ a, const fe* __restrict__ s, size_t n0, size_t h, int right) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n0) return;
+    const size_t m = 2 * h, t = idx / m, i = idx % m;
+    fe v = fe_zero();
+    if (right ? (i >= h) : (i < h)) v = fe_mul<FS>(load_fe_nc(a + (right ? i - h : i + h)), load_fe_nc(s + t));
+    store_fe(sc + idx, v);
+}
+
+template <class FS> static int inner_product(zk_ipa* s, const fe* x, const fe* y, size_t m, fe* d_out) {
+    k_inner_product<FS><<<IP_BLOCKS, IP_THREADS, 0, s->ctx->stream>>>(x, y, m, s->d_part);
+    k_inner_product_final<FS><<<1, IP_BLOCKS, 0, s->ctx->stream>>>(s->d_part, d_out);
+    ZK_CUDA(cudaGetLastError());
+    s->ctx->launches += 2;
+    return ZK_OK;
+}
+
+}  // namespace zkb
+
+template <class FS> static int ipa_expand_and_msm(zk_ipa* s, size_t h, int right, uint64_t out_xyz[12]) {
+    zk_ctx* ctx = s->ctx;
+    k_expand_scalars<FS><<<(unsigned)((s->n0 + 255) / 256), 256, 0, ctx->stream>>>(s->d_sc, s->d_a, s->d_s[s->cur], s->n0, h, right);
+    ZK_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    const size_t len = s->n0 < s->bases->b.n ? s->n0 : s->bases->b.n;   // positions past the SRS are identity padding
+    return ctx_msm_device(ctx, s->bases, 0, len, s->d_sc, /*mont=*/1, 0, out_xyz);
+}
+
+static void ipa_release(zk_ipa* s) {
+    cudaFree(s->d_a); cudaFree(s->d_b); cudaFree(s->d_s[0]); cudaFree(s->d_s[1]); cudaFree(s->d_sc); cudaFree(s->d_part);
+    if (s->h_ip) cudaFreeHost(s->h_ip);
+    delete s;
+}
+
+extern "C" {
+
+int zk_ipa_begin(zk_ctx* ctx, const zk_bases* bases, const uint64_t* a_mont, const uint64_t* b_mont, size_t n, zk_ipa** out) {
+    if (!ctx || !bases || !a_mont || !b_mont || !out) { zk_set_error("ipa_begin: null argument"); return ZK_ERR_INVALID; }
+    if (bases->ctx != ctx) { zk_set_error("ipa_begin: bases belong to another context"); return ZK_ERR_INVALID; }
+    if (n < 2 || (n & (n - 1))) { zk_set_error("ipa_begin: n must be a power of two >= 2 (the reference pads to a power of two, ipa.rs:848-850)"); return ZK_ERR_INVALID; }
+    if (bases->b.n > n || 2 * bases->b.n <= n) { zk_set_error("ipa_begin: n = %zu is not the SRS size %zu rounded up to a power of two", n, bases->b.n); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    zk_ipa* s = new zk_ipa();
+    s->ctx = ctx; s->curve = bases->b.curve; s->n = s->n0 = n; s->bases = bases;
+    const fe one = s->curve == ZK_PALLAS ? fe_one<FqParams>() : fe_one<FpParams>();
+    cudaError_t e = cudaMalloc(&s->d_a, n * sizeof(fe));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_b, n * sizeof(fe));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_s[0], n * sizeof(fe));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_s[1], n * sizeof(fe));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_sc, n * sizeof(fe));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_part, (IP_BLOCKS + 2) * sizeof(fe));
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_ip, 2 * sizeof(fe));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_a, a_mont, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_b, b_mont, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_s[0], &one, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);   // s_0 = (1)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        zk_set_error("ipa_begin: %s", cudaGetErrorString(e));
+        ipa_release(s);
+        return ZK_ERR_CUDA;
+    }
+    *out = s;
+    return ZK_OK;
+}
+
+void zk_ipa_free(zk_ipa* s) {
+    if (!s) return;
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    cudaSetDevice(s->ctx->device);
+    ipa_release(s);
+}
+
+size_t zk_ipa_len(const zk_ipa* s) { return s ? s->n : 0; }
+
+int zk_ipa_round_lr(zk_ipa* s, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12], uint64_t out_ip_l[4], uint64_t out_ip_r[4]) {
+    if (!s || !out_l_xyz || !out_r_xyz || !out_ip_l || !out_ip_r) { zk_set_error("ipa_round_lr: null argument"); return ZK_ERR_INVALID; }
+    if (s->n < 2) { zk_set_error("ipa_round_lr: folding is complete"); return ZK_ERR_INVALID; }
+    zk_ctx* ctx = s->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    const size_t h = s->n / 2;
+    const bool pallas = s->curve == ZK_PALLAS;   // scalar field of Pallas is Fq
+    // inner products <a_hi, b_lo>, <a_lo, b_hi>
+    int rc = pallas ? inner_product<FqParams>(s, s->d_a + h, s->d_b, h, s->d_part + IP_BLOCKS)
+                    : inner_product<FpParams>(s, s->d_a + h, s->d_b, h, s->d_part + IP_BLOCKS);
+    if (rc) return rc;
+    rc = pallas ? inner_product<FqParams>(s, s->d_a, s->d_b + h, h, s->d_part + IP_BLOCKS + 1)
+                : inner_product<FpParams>(s, s->d_a, s->d_b + h, h, s->d_part + IP_BLOCKS + 1);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(s->h_ip, s->d_part + IP_BLOCKS, 2 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = pallas ? ipa_expand_and_msm<FqParams>(s, h, 0, out_l_xyz) : ipa_expand_and_msm<FpParams>(s, h, 0, out_l_xyz);
+    if (rc) return rc;
+    rc = pallas ? ipa_expand_and_msm<FqParams>(s, h, 1, out_r_xyz) : ipa_expand_and_msm<FpParams>(s, h, 1, out_r_xyz);
+    if (rc) return rc;
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_ip_l, &s->h_ip[0], 32);
+    memcpy(out_ip_r, &s->h_ip[1], 32);
+    return ZK_OK;
+}
+
+int zk_ipa_round_fold(zk_ipa* s, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]) {
+    if (!s || !u_mont || !u_inv_mont) { zk_set_error("ipa_round_fold: null argument"); return ZK_ERR_INVALID; }
+    if (s->n < 2) { zk_set_error("ipa_round_fold: folding is complete"); return ZK_ERR_INVALID; }
+    zk_ctx* ctx = s->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    const size_t h = s->n / 2, count = s->n0 / s->n;   // count = 2^j challenges products so far
+    fe u, ui;
+    memcpy(u.v, u_mont, 32);
+    memcpy(ui.v, u_inv_mont, 32);
+    const unsigned blocks = (unsigned)((h + 127) / 128), sblocks = (unsigned)((count + 127) / 128);
+    if (s->curve == ZK_PALLAS) {
+        k_fold_field<FqParams><<<blocks, 128, 0, ctx->stream>>>(s->d_a, h, ui);
+        k_fold_field<FqParams><<<blocks, 128, 0, ctx->stream>>>(s->d_b, h, u);
+        k_expand_challenges<FqParams><<<sblocks, 128, 0, ctx->stream>>>(s->d_s[s->cur], s->d_s[s->cur ^ 1], count, u);
+    } else {
+        k_fold_field<FpParams><<<blocks, 128, 0, ctx->stream>>>(s->d_a, h, ui);
+        k_fold_field<FpParams><<<blocks, 128, 0, ctx->stream>>>(s->d_b, h, u);
+        k_expand_challenges<FpParams><<<sblocks, 128, 0, ctx->stream>>>(s->d_s[s->cur], s->d_s[s->cur ^ 1], count, u);
+    }
+    ZK_CUDA(cudaGetLastError());
+    ctx->launches += 3;
+    s->cur ^= 1;
+    s->n = h;
+    return ZK_OK;
+}
+
+// Current state: copies min(len, capacity) leading elements of a and b (Montgomery); out_g_xyz (optional) receives the first
+// current folded base g_j[0] in Jacobian form — after the last fold that is g0 = <b_poly_coefficients(chals), g>, the
+// proof's `sg` (one MSM over the resident table).
+int zk_ipa_read(zk_ipa* s, uint64_t* out_a, uint64_t* out_b, size_t capacity, uint64_t out_g_xyz[12]) {
+    if (!s) { zk_set_error("ipa_read: null argument"); return ZK_ERR_INVALID; }
+    zk_ctx* ctx = s->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    const size_t m = s->n < capacity ? s->n : capacity;
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_a && m) ZK_CUDA(cudaMemcpy(out_a, s->d_a, m * sizeof(fe), cudaMemcpyDeviceToHost));
+    if (out_b && m) ZK_CUDA(cudaMemcpy(out_b, s->d_b, m * sizeof(fe), cudaMemcpyDeviceToHost));
+    if (out_g_xyz) {
+        // g_j[0] = sum_t s_j[t] g[t * m_j]: scalars a == (1, 0, 0, ...) per block — expand with a one-hot "a"
+        if (s->n != 1) { zk_set_error("ipa_read: the folded base is available after the last round only"); return ZK_ERR_INVALID; }
+        const size_t len = s->n0 < s->bases->b.n ? s->n0 : s->bases->b.n;
+        return ctx_msm_device(ctx, s->bases, 0, len, s->d_s[s->cur], /*mont=*/1, 0, out_g_xyz);
+    }
+    return ZK_OK;
+}
+
+}  // extern "C"

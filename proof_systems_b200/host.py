@@ -110,6 +110,64 @@ class SRS:
         return self.mask_custom(self.commit_evaluations_non_hiding(domain_size, evals), blinders)
 
 
+class IpaRounds:
+    """The folding loop of SRS::open (poly-commitment/src/ipa.rs:929-1007) with a and b resident on the device and the bases
+    taken from the resident SRS table (`bases` = ctx.upload_bases(curve, srs.g)); see csrc/ipa.cu.
+
+    The caller owns the sponge: per round it takes `lr()` -> (<a_hi,g_lo>, <a_lo,g_hi>, <a_hi,b_lo>, <a_lo,b_hi>), finishes
+    L and R with its blinders (rand_l * h + <a_hi,b_lo> * u_base, ipa.rs:943-961), absorbs them, squeezes u and calls
+    `fold(u, u_inv)`.  After log2(n) rounds `state()` is (a0, b0) and `sg()` the folded base g0."""
+
+    def __init__(self, ctx: Context, bases, a_mont, b_mont):
+        a, b = _np_u64(a_mont, (4,)), _np_u64(b_mont, (4,))
+        n = 1 << max(1, (len(bases) - 1).bit_length())          # ipa.rs:848-850: padded_length
+        if a.shape[0] > n or b.shape[0] > n:
+            raise ValueError("a and b must not be longer than the padded SRS")
+        pad = lambda v: np.concatenate([v, np.zeros((n - v.shape[0], 4), dtype=np.uint64)]) if v.shape[0] < n else v
+        a, b = pad(a), pad(b)                                    # ipa.rs:858-862: a padded with zeros
+        self.ctx, self.curve, self.bases = ctx, bases.curve, bases
+        self._h = ctypes.c_void_p()
+        check(lib().zk_ipa_begin(ctx._h, bases._h, _ptr(a), _ptr(b), n, ctypes.byref(self._h)))
+
+    def __len__(self):
+        return int(lib().zk_ipa_len(self._h))
+
+    def lr(self):
+        l, r = np.zeros(12, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+        ipl, ipr = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+        check(lib().zk_ipa_round_lr(self._h, l.ctypes.data_as(_u64p), r.ctypes.data_as(_u64p), ipl.ctypes.data_as(_u64p), ipr.ctypes.data_as(_u64p)))
+        return l, r, ipl, ipr
+
+    def fold(self, u_mont, u_inv_mont):
+        u = np.ascontiguousarray(u_mont, dtype=np.uint64).reshape(4)
+        ui = np.ascontiguousarray(u_inv_mont, dtype=np.uint64).reshape(4)
+        check(lib().zk_ipa_round_fold(self._h, u.ctypes.data_as(_u64p), ui.ctypes.data_as(_u64p)))
+
+    def state(self):
+        n = len(self)
+        a, b = np.zeros((n, 4), dtype=np.uint64), np.zeros((n, 4), dtype=np.uint64)
+        check(lib().zk_ipa_read(self._h, _ptr(a), _ptr(b), n, None))
+        return a, b
+
+    def sg(self) -> np.ndarray:
+        """g0 after the last fold, Jacobian [12]"""
+        out = np.zeros(12, dtype=np.uint64)
+        check(lib().zk_ipa_read(self._h, None, None, 0, out.ctypes.data_as(_u64p)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zk_ipa_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
 class Radix2EvaluationDomain:
     """ark_poly::Radix2EvaluationDomain::<F>::new(size) on the device.  `field` is ZK_FP or ZK_FQ."""
 
