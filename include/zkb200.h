@@ -81,6 +81,11 @@ int zk_bases_window_bits(const zk_bases* bases);
  * srs/pallas.srs / srs/vesta.srs through SerdeAs (utils/src/serialization.rs:65-106): 32-byte LE canonical x, then a flag
  * byte (bit 7: y is the larger root, bit 6: infinity) — to affine Montgomery points.  ZK_ERR_INVALID if some x is off-curve. */
 int zk_points_decompress(zk_ctx* ctx, int curve_id, const uint8_t* in33, size_t n, uint64_t* out_xy);
+/* The other two codecs of utils/src/serialization.rs: the 65-byte uncompressed, unchecked form of srs/test_*.srs
+ * (SerdeAsUnchecked, :108-146: x || y || flag byte, bit 6 = infinity; no curve check — ZK_ERR_INVALID only for a coordinate
+ * >= the modulus), and the inverse of zk_points_decompress (the form PolyComm / OpeningProof serialise to, :65-84). */
+int zk_points_from_uncompressed(zk_ctx* ctx, int curve_id, const uint8_t* in65, size_t n, uint64_t* out_xy);
+int zk_points_compress(zk_ctx* ctx, int curve_id, const uint64_t* xy_mont, size_t n, uint8_t* out33);
 
 /* ------------------------------------------------------------------ MSM
  * zk_msm == <G::Group as VariableBaseMSM>::msm_bigint(&bases[off..off+n], scalars)   (scalars_are_mont = 0: canonical

@@ -58,6 +58,8 @@ def lib() -> ctypes.CDLL:
     L.zk_bases_len.restype = sz
     L.zk_bases_window_bits.argtypes = [vp]
     L.zk_points_decompress.argtypes = [vp, i, vp, sz, _u64p]
+    L.zk_points_from_uncompressed.argtypes = [vp, i, vp, sz, _u64p]
+    L.zk_points_compress.argtypes = [vp, i, vp, sz, vp]
     L.zk_msm.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
     L.zk_msm_dev.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
     L.zk_msm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i, i, _u64p]
@@ -174,6 +176,22 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ MSM
+    def points_from_uncompressed(self, curve: int, raw65) -> np.ndarray:
+        """uint8 [n, 65] ark uncompressed points (the srs/test_*.srs form) -> uint64 [n, 8] affine Montgomery"""
+        raw = np.ascontiguousarray(raw65, dtype=np.uint8)
+        if raw.ndim != 2 or raw.shape[1] != 65:
+            raise ValueError("expected uint8 [n, 65]")
+        out = np.zeros((raw.shape[0], 8), dtype=np.uint64)
+        check(lib().zk_points_from_uncompressed(self._h, curve, _ptr(raw), raw.shape[0], out.ctypes.data_as(_u64p)))
+        return out
+
+    def compress_points(self, curve: int, points) -> np.ndarray:
+        """uint64 [n, 8] affine Montgomery -> uint8 [n, 33] ark compressed points (what PolyComm / OpeningProof serialise to)"""
+        pts = _np_u64(points, (8,))
+        out = np.zeros((pts.shape[0], 33), dtype=np.uint8)
+        check(lib().zk_points_compress(self._h, curve, _ptr(pts), pts.shape[0], _ptr(out)))
+        return out
+
     def upload_bases(self, curve: int, points, window_bits: int = -1) -> "Bases":
         return Bases(self, curve, points, window_bits)
 

@@ -15,6 +15,8 @@
 namespace zkb {
 
 template <class F> int points_decompress(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st);   // decompress.cu
+template <class F> int points_from_uncompressed(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st);
+template <class F> int points_compress(const affine_t* d_in, uint8_t* d_out, size_t n, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 void zk_set_error(const char* fmt, ...) {
@@ -304,33 +306,61 @@ void zk_bases_free(zk_bases* bases) {
 size_t zk_bases_len(const zk_bases* bases) { return bases ? bases->b.n : 0; }
 int zk_bases_window_bits(const zk_bases* bases) { return bases ? (int)bases->b.c : 0; }
 
-// ark-serialize compressed points (33 bytes each) -> affine Montgomery points; host pointers
-int zk_points_decompress(zk_ctx* ctx, int curve_id, const uint8_t* in33, size_t n, uint64_t* out_xy) {
-    if (!ctx || (!in33 && n) || (!out_xy && n)) { zk_set_error("points_decompress: null argument"); return ZK_ERR_INVALID; }
-    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("points_decompress: unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
+// Point codecs between the reference's serialised forms and affine Montgomery points; host pointers.
+//   mode 0: 33-byte compressed   -> affine   (decompression: one square root per point)
+//   mode 1: 65-byte uncompressed -> affine   (unchecked, as SerdeAsUnchecked)
+//   mode 2: affine -> 33-byte compressed
+static int points_codec(zk_ctx* ctx, int curve_id, int mode, const void* in, size_t n, void* out, const char* what) {
+    if (!ctx || (!in && n) || (!out && n)) { zk_set_error("%s: null argument", what); return ZK_ERR_INVALID; }
+    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("%s: unknown curve_id %d", what, curve_id); return ZK_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return ZK_OK;
-    uint8_t* d_in = nullptr;
-    affine_t* d_out = nullptr;
+    const size_t in_bytes = (mode == 0 ? 33 : mode == 1 ? 65 : sizeof(affine_t)) * n, out_bytes = (mode == 2 ? 33 : sizeof(affine_t)) * n;
+    void *d_in = nullptr, *d_out = nullptr;
     unsigned* d_bad = nullptr;
     unsigned bad = 0;
-    ZK_CUDA(cudaMalloc(&d_in, 33 * n));
-    ZK_CUDA(cudaMalloc(&d_out, n * sizeof(affine_t)));
-    ZK_CUDA(cudaMalloc(&d_bad, sizeof(unsigned)));
-    ZK_CUDA(cudaMemcpyAsync(d_in, in33, 33 * n, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = curve_id == ZK_PALLAS ? points_decompress<FpParams>(d_in, d_out, n, d_bad, ctx->stream)
-                                   : points_decompress<FqParams>(d_in, d_out, n, d_bad, ctx->stream);
-    if (rc == ZK_OK) {
-        ctx->launches += 1;
-        cudaMemcpyAsync(out_xy, d_out, n * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(&bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { zk_set_error("points_decompress: %s", cudaGetErrorString(e)); rc = ZK_ERR_CUDA; }
+    cudaError_t e = cudaMalloc(&d_in, in_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_bad, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(unsigned), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = ZK_OK;
+    if (e == cudaSuccess) {
+        const bool pallas = curve_id == ZK_PALLAS;
+        if (mode == 0)
+            rc = pallas ? points_decompress<FpParams>((const uint8_t*)d_in, (affine_t*)d_out, n, d_bad, ctx->stream)
+                        : points_decompress<FqParams>((const uint8_t*)d_in, (affine_t*)d_out, n, d_bad, ctx->stream);
+        else if (mode == 1)
+            rc = pallas ? points_from_uncompressed<FpParams>((const uint8_t*)d_in, (affine_t*)d_out, n, d_bad, ctx->stream)
+                        : points_from_uncompressed<FqParams>((const uint8_t*)d_in, (affine_t*)d_out, n, d_bad, ctx->stream);
+        else
+            rc = pallas ? points_compress<FpParams>((const affine_t*)d_in, (uint8_t*)d_out, n, ctx->stream)
+                        : points_compress<FqParams>((const affine_t*)d_in, (uint8_t*)d_out, n, ctx->stream);
+        if (rc == ZK_OK) {
+            ctx->launches += 1;
+            e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
     }
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_bad);
-    if (rc == ZK_OK && bad) { zk_set_error("points_decompress: %u of %zu x-coordinates are not on the curve", bad, n); return ZK_ERR_INVALID; }
+    if (e != cudaSuccess) { zk_set_error("%s: %s", what, cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+    if (rc == ZK_OK && bad) {
+        zk_set_error(mode == 0 ? "%s: %u of %zu x-coordinates are not on the curve" : "%s: %u of %zu points have a non-canonical coordinate", what, bad, n);
+        return ZK_ERR_INVALID;
+    }
     return rc;
+}
+
+int zk_points_decompress(zk_ctx* ctx, int curve_id, const uint8_t* in33, size_t n, uint64_t* out_xy) {
+    return points_codec(ctx, curve_id, 0, in33, n, out_xy, "points_decompress");
+}
+int zk_points_from_uncompressed(zk_ctx* ctx, int curve_id, const uint8_t* in65, size_t n, uint64_t* out_xy) {
+    return points_codec(ctx, curve_id, 1, in65, n, out_xy, "points_from_uncompressed");
+}
+int zk_points_compress(zk_ctx* ctx, int curve_id, const uint64_t* xy_mont, size_t n, uint8_t* out33) {
+    return points_codec(ctx, curve_id, 2, xy_mont, n, out33, "points_compress");
 }
 
 // ---------------------------------------------------------------------------------------------- MSM

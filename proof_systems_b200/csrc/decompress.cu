@@ -63,6 +63,19 @@ template <class F> __device__ bool fe_canonical_gt(const fe& a, const fe& b) {
     return false;
 }
 
+__device__ __forceinline__ fe load_le_bytes(const uint8_t* p) {
+    fe r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+    return r;
+}
+__device__ __forceinline__ void store_le_bytes(uint8_t* p, const fe& a) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        p[4 * k] = (uint8_t)a.v[k]; p[4 * k + 1] = (uint8_t)(a.v[k] >> 8); p[4 * k + 2] = (uint8_t)(a.v[k] >> 16); p[4 * k + 3] = (uint8_t)(a.v[k] >> 24);
+    }
+}
+
 template <class F> __global__ void __launch_bounds__(128) k_decompress(const uint8_t* __restrict__ in, affine_t* out, size_t n, unsigned* bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -72,9 +85,7 @@ template <class F> __global__ void __launch_bounds__(128) k_decompress(const uin
     r.x = fe_zero();
     r.y = fe_zero();
     if (!(flags & 0x40)) {
-        fe xc;
-#pragma unroll
-        for (int k = 0; k < 8; k++) xc.v[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+        const fe xc = load_le_bytes(p);
         const fe x = fe_to_mont<F>(xc);
         fe five = fe_zero();
         five.v[0] = 5;
@@ -89,6 +100,57 @@ template <class F> __global__ void __launch_bounds__(128) k_decompress(const uin
     }
     store_affine(out + i, r);
 }
+
+// ark-serialize uncompressed, unchecked (SerdeAsUnchecked, utils/src/serialization.rs:108-146; the srs/test_*.srs layout):
+// 32 B LE canonical x || 32 B LE canonical y || flag byte (bit 6 = infinity).  No curve check, as in the reference.
+template <class F> __global__ void __launch_bounds__(128) k_from_uncompressed(const uint8_t* __restrict__ in, affine_t* out, size_t n, unsigned* bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = in + 65 * i;
+    affine_t r;
+    r.x = fe_zero();
+    r.y = fe_zero();
+    if (!(p[64] & 0x40)) {
+        const fe xc = load_le_bytes(p), yc = load_le_bytes(p + 32);
+        if (!fe_lt_modulus<F>(xc) || !fe_lt_modulus<F>(yc)) atomicAdd(bad, 1u);   // not a canonical field element
+        r.x = fe_to_mont<F>(xc);
+        r.y = fe_to_mont<F>(yc);
+    }
+    store_affine(out + i, r);
+}
+
+// affine Montgomery -> 33-byte compressed form (the inverse of k_decompress): what PolyComm / OpeningProof serialise to
+// (utils/src/serialization.rs:65-84).  The identity is x = 0, flags = 0x40.
+template <class F> __global__ void __launch_bounds__(128) k_compress(const affine_t* __restrict__ in, uint8_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const affine_t a = load_affine_nc(in + i);
+    uint8_t* p = out + 33 * i;
+    if (affine_is_inf(a)) {
+        store_le_bytes(p, fe_zero());
+        p[32] = 0x40;
+        return;
+    }
+    store_le_bytes(p, fe_from_mont<F>(a.x));
+    p[32] = fe_canonical_gt<F>(a.y, fe_neg<F>(a.y)) ? 0x80 : 0x00;
+}
+
+template <class F> int points_from_uncompressed(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st) {
+    ZK_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), st));
+    if (n) k_from_uncompressed<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_in, d_out, n, d_bad);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+template int points_from_uncompressed<FpParams>(const uint8_t*, affine_t*, size_t, unsigned*, cudaStream_t);
+template int points_from_uncompressed<FqParams>(const uint8_t*, affine_t*, size_t, unsigned*, cudaStream_t);
+
+template <class F> int points_compress(const affine_t* d_in, uint8_t* d_out, size_t n, cudaStream_t st) {
+    if (n) k_compress<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_in, d_out, n);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+template int points_compress<FpParams>(const affine_t*, uint8_t*, size_t, cudaStream_t);
+template int points_compress<FqParams>(const affine_t*, uint8_t*, size_t, cudaStream_t);
 
 template <class F> int points_decompress(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st) {
     ZK_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), st));

@@ -145,6 +145,15 @@ template <class F> ZK_HD void fe_cond_sub(fe& t) {
     for (int i = 0; i < 8; i++) t.v[i] = borrow ? t.v[i] : d[i];
 }
 
+// a < m ?  (is the 256-bit integer a canonical field element)
+template <class F> ZK_HD bool fe_lt_modulus(const fe& a) {
+    const uint32_t m[8] = {1u, F::M1, F::M2, F::M3, 0u, 0u, 0u, M7};
+    for (int i = 7; i >= 0; i--) {
+        if (a.v[i] != m[i]) return a.v[i] < m[i];
+    }
+    return false;
+}
+
 template <class F> ZK_HD fe fe_add(const fe& a, const fe& b) {
     fe r;
     r.v[0] = add_cc(a.v[0], b.v[0]);

@@ -39,6 +39,20 @@ class SRS:
         self._h = ctypes.c_void_p()
         check(lib().zk_srs_create(ctx._h, curve, _ptr(self.g), self.g.shape[0], self.h.ctypes.data_as(_u64p), window_bits, ctypes.byref(self._h)))
 
+    @classmethod
+    def from_file(cls, ctx: Context, curve: int, path: str, window_bits: int = -1, lagrange: bool = True) -> "SRS":
+        """Load srs/{pallas,vesta}.srs or srs/test_{pallas,vesta}.srs (precomputed_srs.rs:76-91 get_srs / get_srs_test): the points
+        are decoded on the device; the Lagrange bases stored in a test file populate the cache (single-chunk bases only)."""
+        from . import srs_file
+        f = srs_file.read_srs(path)
+        dec = ctx.decompress_points if f.compressed else ctx.points_from_uncompressed
+        srs = cls(ctx, curve, dec(curve, f.g), dec(curve, f.h.reshape(1, -1))[0], window_bits)
+        if lagrange:
+            for n, basis in f.lagrange_bases.items():
+                if basis.shape[1] == 1:
+                    srs.add_lagrange_basis(n, ctx.points_from_uncompressed(curve, basis[:, 0]))
+        return srs
+
     def close(self):
         if getattr(self, "_h", None):
             lib().zk_srs_destroy(self._h)

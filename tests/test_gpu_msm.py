@@ -114,6 +114,24 @@ def test_degenerate_all_ones_witness_column(ctx, orc, pallas_srs):
     bases.free()
 
 
+@pytest.mark.parametrize("sparsity", [0.05, 0.5, 0.99])
+@pytest.mark.parametrize("bitlen", [16, 64, 128, 256])
+def test_sparse_and_short_scalars(ctx, orc, vesta_srs, sparsity, bitlen):
+    """The scalar distributions of the reference's `IPA Commit Evaluations` bench (poly-commitment/benches/ipa.rs:69-92):
+    a fraction of the scalars non-zero, those reduced to `bitlen` bits — the high windows are empty, the low ones dense."""
+    srs = vesta_srs
+    n = 2048
+    rng = np.random.default_rng(int(sparsity * 100) * 1000 + bitlen)
+    vals = orc.limbs_to_ints(orc.random_scalars(srs.scalar, n, seed=bitlen))
+    keep = rng.random(n) < sparsity
+    sc = orc.ints_to_limbs([(v % (1 << bitlen)) if k else 0 for v, k in zip(vals, keep)])
+    want = orc.msm(srs.cid, srs.g[:n], sc)
+    for wb in (-1, 0, 7):
+        bases = ctx.upload_bases(srs.cid, srs.g[:n], window_bits=wb)
+        assert np.array_equal(ctx.msm_affine(bases, sc), want), wb
+        bases.free()
+
+
 def test_config2_2_16_pallas(ctx, orc, pallas_srs):
     """BASELINE config 2: 2^16-point Pallas MSM on the real SRS, w = 16 table and the tuned window; one answer is
     pinned by srs/test_pallas.srs (lagrange_bases[65536][i]), the random-scalar answer by the oracle."""

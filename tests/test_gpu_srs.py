@@ -119,3 +119,50 @@ def test_device_point_decompression(ctx, orc, request, name):
     assert bad is not None
     with pytest.raises(zk.ZkError):
         ctx.decompress_points(g.cid, bad)
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_point_codecs_round_trip_the_reference_bytes(ctx, orc, request, name):
+    """compress(decompress(raw)) == raw on every generator the reference ships (srs/*.srs bytes), and the uncompressed form of
+    srs/test_*.srs decodes to the same points (utils/src/serialization.rs:65-146)."""
+    G = request.getfixturevalue(name)
+    pts = ctx.decompress_points(G.cid, G.g_cmp)
+    assert np.array_equal(ctx.compress_points(G.cid, pts), G.g_cmp)
+    raw65 = np.concatenate([G.g_xy_canon, np.zeros((2048, 1), dtype=np.uint8)], axis=1)
+    assert np.array_equal(ctx.points_from_uncompressed(G.cid, raw65), pts[:2048])
+    # the identity: flag bit 6
+    ident = np.zeros((1, 33), dtype=np.uint8)
+    ident[0, 32] = 0x40
+    assert not np.any(ctx.decompress_points(G.cid, ident))
+    assert np.array_equal(ctx.compress_points(G.cid, np.zeros((1, 8), dtype=np.uint64)), ident)
+    raw65[5, 64] = 0x40
+    assert not np.any(ctx.points_from_uncompressed(G.cid, raw65[:8])[5])
+    # a coordinate >= the modulus is rejected
+    raw65[6, :32] = 0xFF
+    with pytest.raises(zk.ZkError):
+        ctx.points_from_uncompressed(G.cid, raw65[:8])
+
+
+def test_srs_from_file(ctx, orc, vesta_srs, tmp_path):
+    """get_srs_test (precomputed_srs.rs:84-91): g, h and the stored Lagrange bases straight from a test_*.srs-format file;
+    commit_evaluations then uses the file's basis, which equals the one built on the device."""
+    from proof_systems_b200 import srs_file
+    G = vesta_srs
+    n = 1024
+    flag = np.zeros((n, 1), dtype=np.uint8)
+    g65 = np.concatenate([G.g_xy_canon[:n], flag], axis=1)
+    h65 = np.concatenate([G.h_xy_canon, [0]]).astype(np.uint8)
+    bases = {m: np.concatenate([G.lag_small_canon[m - 1:2 * m - 1], flag[:m]], axis=1).reshape(m, 1, 65) for m in (1, 4, n)}
+    path = str(tmp_path / "test_vesta.srs")
+    srs_file.write_srs(path, srs_file.SrsFile(g=g65, h=h65, lagrange_bases=bases))
+    srs = zk.SRS.from_file(ctx, G.cid, path)
+    assert srs.max_poly_size() == n and np.array_equal(srs.g, G.g[:n]) and np.array_equal(srs.h, G.mont_points(G.h_xy_canon)[0])
+    ev = orc.to_mont(G.scalar, orc.random_scalars(G.scalar, n, seed=77))
+    got = srs.commit_evaluations_non_hiding(n, ev)
+    want = orc.msm_mont(G.cid, G.lagrange_small(n), ev)
+    assert np.array_equal(got.chunks[0], want)
+    assert np.array_equal(srs.get_lagrange_basis_from_domain_size(n), G.lagrange_small(n))   # served from the file's copy
+    fresh = zk.SRS.from_file(ctx, G.cid, path, lagrange=False)
+    assert np.array_equal(fresh.get_lagrange_basis_from_domain_size(n), G.lagrange_small(n))  # built on the device
+    srs.close()
+    fresh.close()
