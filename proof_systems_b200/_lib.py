@@ -79,6 +79,7 @@ def lib() -> ctypes.CDLL:
     L.zk_srs_get_lagrange_basis.argtypes = [vp, sz, _u64p, sz]
     L.zk_srs_commit_non_hiding.argtypes = [vp, vp, sz, sz, _u64p, sz, ctypes.POINTER(sz)]
     L.zk_srs_commit_evaluations_non_hiding.argtypes = [vp, sz, vp, sz, _u64p]
+    L.zk_srs_commit_evaluations_batch.argtypes = [vp, sz, vp, sz, _u64p]
     L.zk_srs_mask_custom.argtypes = [vp, vp, sz, vp, sz, _u64p]
     L.zk_ipa_begin.argtypes = [vp, vp, vp, vp, sz, ctypes.POINTER(vp)]
     L.zk_ipa_free.argtypes = [vp]

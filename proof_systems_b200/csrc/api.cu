@@ -71,6 +71,85 @@ int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, con
     return ZK_OK;
 }
 
+static int ctx_lanes_init(zk_ctx* ctx) {
+    if (ctx->ev_fork) return ZK_OK;
+    for (int l = 0; l < zk_ctx::SIDE_LANES; l++) {
+        ZK_CUDA(cudaStreamCreateWithFlags(&ctx->side[l], cudaStreamNonBlocking));
+        ctx->ws_side[l].sm_count = ctx->ws.sm_count;
+        ctx->ws_side[l].defer_sync = true;
+    }
+    for (int l = 0; l < 1 + zk_ctx::SIDE_LANES; l++)
+        for (int s = 0; s < 2; s++) ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[l][s], cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    return ZK_OK;
+}
+
+int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, const size_t* offs, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
+                 uint64_t* out_xyz) {
+    if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
+    if (k == 0) return ZK_OK;
+    // one lane when profiling (stage events are per workspace) or when the caller pinned the task length
+    const int lanes = (k == 1 || ctx->profile || ctx->lanes <= 1) ? 1 : (int)std::min<size_t>(k, (size_t)std::min(ctx->lanes, 1 + zk_ctx::SIDE_LANES));
+    if (lanes == 1) {
+        for (size_t j = 0; j < k; j++) {
+            int rc = ctx_msm_device(ctx, bases, offs[j], n, d_scalars[j], mont, window_bits, out_xyz + 12 * j);
+            if (rc) return rc;
+        }
+        return ZK_OK;
+    }
+    int rc = ctx_lanes_init(ctx);
+    if (rc) return rc;
+    const bool pallas = bases->b.curve == ZK_PALLAS;
+    ZK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));            // the scalars are ready on the main stream
+    for (int l = 1; l < lanes; l++) ZK_CUDA(cudaStreamWaitEvent(ctx->side[l - 1], ctx->ev_fork, 0));
+    std::vector<MsmResultShape> shapes(k);
+    auto lane_ws = [&](int l) -> MsmWorkspace& { return l == 0 ? ctx->ws : ctx->ws_side[l - 1]; };
+    auto collect = [&](size_t j) -> int {
+        const int l = (int)(j % lanes), slot = (int)((j / lanes) & 1);
+        ZK_CUDA(cudaEventSynchronize(ctx->ev_lane[l][slot]));
+        host::hxyzz r = host::identity();
+        const MsmResultShape& sh = shapes[j];
+        if (sh.groups) {
+            const xyzz_t* h = lane_ws(l).h_bitsums + (size_t)slot * sh.groups * sh.c;
+            r = pallas ? msm_finish_t<host::HFp>(h, sh.c, sh.groups) : msm_finish_t<host::HFq>(h, sh.c, sh.groups);
+        }
+        xyzz_to_jac_out(bases->b.curve, r, out_xyz + 12 * j);
+        return ZK_OK;
+    };
+    const bool keep_defer = ctx->ws.defer_sync;
+    ctx->ws.defer_sync = true;
+    size_t collected = 0;
+    rc = ZK_OK;
+    for (size_t j = 0; j < k && rc == ZK_OK; j++) {
+        const int l = (int)(j % lanes), slot = (int)((j / lanes) & 1);
+        // the slot's previous user is MSM j - 2*lanes: finish it on the host before its pinned copy is overwritten
+        while (rc == ZK_OK && j >= 2 * (size_t)lanes && collected <= j - 2 * (size_t)lanes) rc = collect(collected++);
+        if (rc) break;
+        MsmWorkspace& ws = lane_ws(l);
+        cudaStream_t st = l == 0 ? ctx->stream : ctx->side[l - 1];
+        ws.h_slot = (unsigned)slot;
+        ws.chunk = ctx->ws.chunk;
+        unsigned nl = 0;
+        rc = pallas ? msm_run<FpParams, FqParams>(bases->b, offs[j], n, d_scalars[j], mont != 0, (unsigned)window_bits, ws, st, &shapes[j], &nl)
+                    : msm_run<FqParams, FpParams>(bases->b, offs[j], n, d_scalars[j], mont != 0, (unsigned)window_bits, ws, st, &shapes[j], &nl);
+        ctx->launches += nl;
+        if (rc == ZK_OK && cudaEventRecord(ctx->ev_lane[l][slot], st) != cudaSuccess) { zk_set_error("msm: cudaEventRecord failed"); rc = ZK_ERR_CUDA; }
+    }
+    ctx->ws.defer_sync = keep_defer;
+    ctx->ws.h_slot = 0;
+    if (rc != ZK_OK) {   // drain whatever was enqueued before reporting
+        cudaStreamSynchronize(ctx->stream);
+        for (int l = 1; l < lanes; l++) cudaStreamSynchronize(ctx->side[l - 1]);
+        return rc;
+    }
+    while (collected < k) {
+        rc = collect(collected++);
+        if (rc) return rc;
+    }
+    // every lane has been waited for through its events: later work on the main stream is ordered after all of it
+    return ZK_OK;
+}
+
 int ctx_ensure(void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes) return ZK_OK;
     if (*p) cudaFree(*p);
@@ -229,6 +308,13 @@ void zk_ctx_destroy(zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     msm_workspace_free(ctx->ws);
+    for (int l = 0; l < zk_ctx::SIDE_LANES; l++) {
+        if (ctx->side[l]) { cudaStreamSynchronize(ctx->side[l]); cudaStreamDestroy(ctx->side[l]); }
+        msm_workspace_free(ctx->ws_side[l]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (auto& le : ctx->ev_lane) for (auto& e : le) if (e) cudaEventDestroy(e);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->d_ntt) cudaFree(ctx->d_ntt);
     if (ctx->d_ntt_tmp) cudaFree(ctx->d_ntt_tmp);
@@ -262,6 +348,11 @@ int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value) {
     if (!strcmp(name, "msm_chunk")) {
         if (value < 0 || value > 4096) { zk_set_error("set_option: msm_chunk %ld outside [0, 4096]", value); return ZK_ERR_INVALID; }
         ctx->ws.chunk = (uint32_t)value;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "msm_lanes")) {
+        if (value < 1 || value > 1 + zk_ctx::SIDE_LANES) { zk_set_error("set_option: msm_lanes %ld outside [1, %d]", value, 1 + zk_ctx::SIDE_LANES); return ZK_ERR_INVALID; }
+        ctx->lanes = (int)value;
         return ZK_OK;
     }
     zk_set_error("set_option: unknown option '%s'", name);
@@ -392,11 +483,10 @@ int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const
         if (n) ZK_CUDA(cudaMemcpyAsync(ctx->d_scalars, scalars, k * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
         d_sc = ctx->d_scalars;
     }
-    for (size_t j = 0; j < k; j++) {
-        rc = ctx_msm_device(ctx, bases, off, n, d_sc + j * n, scalars_are_mont, window_bits, out_xyz + 12 * j);
-        if (rc) return rc;
-    }
-    return ZK_OK;
+    std::vector<size_t> offs(k, off);
+    std::vector<const fe*> scs(k);
+    for (size_t j = 0; j < k; j++) scs[j] = d_sc + j * n;
+    return ctx_msm_many(ctx, bases, offs.data(), n, scs.data(), k, scalars_are_mont, window_bits, out_xyz);
 }
 
 int zk_msm(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, int scalars_are_mont, int window_bits, uint64_t out_xyz[12]) {

@@ -28,11 +28,11 @@ struct zk_ipa {
     const zk_bases* bases = nullptr;
     fe* d_s[2] = {nullptr, nullptr};   // b_poly_coefficients of the challenges so far (ping-pong), Montgomery
     int cur = 0;
-    fe* d_sc = nullptr;     // expanded MSM scalars, n0 entries, Montgomery
+    fe* d_sc = nullptr;     // expanded MSM scalars of L and of R, 2 x n0 entries, Montgomery
     fe* d_a = nullptr;
     fe* d_b = nullptr;
     fe* d_part = nullptr;   // inner-product partials
-    fe* h_ip = nullptr;     // pinned: two field elements
+    fe* h_ip = nullptr;     // pinned (the context's scratch): two field elements
 };
 
 namespace zkb {
@@ -100,18 +100,27 @@ template <class FS> static int inner_product(zk_ipa* s, const fe* x, const fe* y
 
 }  // namespace zkb
 
-template <class FS> static int ipa_expand_and_msm(zk_ipa* s, size_t h, int right, uint64_t out_xyz[12]) {
+// L and R of one round: both scalar vectors are expanded on the main stream, the two MSMs run on two lanes
+template <class FS> static int ipa_expand_and_msm(zk_ipa* s, size_t h, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12]) {
     zk_ctx* ctx = s->ctx;
-    k_expand_scalars<FS><<<(unsigned)((s->n0 + 255) / 256), 256, 0, ctx->stream>>>(s->d_sc, s->d_a, s->d_s[s->cur], s->n0, h, right);
+    const unsigned blocks = (unsigned)((s->n0 + 255) / 256);
+    k_expand_scalars<FS><<<blocks, 256, 0, ctx->stream>>>(s->d_sc, s->d_a, s->d_s[s->cur], s->n0, h, 0);
+    k_expand_scalars<FS><<<blocks, 256, 0, ctx->stream>>>(s->d_sc + s->n0, s->d_a, s->d_s[s->cur], s->n0, h, 1);
     ZK_CUDA(cudaGetLastError());
-    ctx->launches += 1;
+    ctx->launches += 2;
     const size_t len = s->n0 < s->bases->b.n ? s->n0 : s->bases->b.n;   // positions past the SRS are identity padding
-    return ctx_msm_device(ctx, s->bases, 0, len, s->d_sc, /*mont=*/1, 0, out_xyz);
+    const size_t offs[2] = {0, 0};
+    const fe* scs[2] = {s->d_sc, s->d_sc + s->n0};
+    uint64_t out[24];
+    int rc = ctx_msm_many(ctx, s->bases, offs, len, scs, 2, /*mont=*/1, 0, out);
+    if (rc) return rc;
+    memcpy(out_l_xyz, out, 96);
+    memcpy(out_r_xyz, out + 12, 96);
+    return ZK_OK;
 }
 
 static void ipa_release(zk_ipa* s) {
-    cudaFree(s->d_a); cudaFree(s->d_b); cudaFree(s->d_s[0]); cudaFree(s->d_s[1]); cudaFree(s->d_sc); cudaFree(s->d_part);
-    if (s->h_ip) cudaFreeHost(s->h_ip);
+    cudaFree(s->d_a);
     delete s;
 }
 
@@ -127,13 +136,13 @@ int zk_ipa_begin(zk_ctx* ctx, const zk_bases* bases, const uint64_t* a_mont, con
     zk_ipa* s = new zk_ipa();
     s->ctx = ctx; s->curve = bases->b.curve; s->n = s->n0 = n; s->bases = bases;
     const fe one = s->curve == ZK_PALLAS ? fe_one<FqParams>() : fe_one<FpParams>();
-    cudaError_t e = cudaMalloc(&s->d_a, n * sizeof(fe));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_b, n * sizeof(fe));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_s[0], n * sizeof(fe));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_s[1], n * sizeof(fe));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_sc, n * sizeof(fe));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_part, (IP_BLOCKS + 2) * sizeof(fe));
-    if (e == cudaSuccess) e = cudaMallocHost(&s->h_ip, 2 * sizeof(fe));
+    // one device allocation: a | b | s0 | s1 | sc_L | sc_R | partials
+    cudaError_t e = cudaMalloc(&s->d_a, (6 * n + IP_BLOCKS + 2) * sizeof(fe));
+    if (e == cudaSuccess) {
+        s->d_b = s->d_a + n; s->d_s[0] = s->d_a + 2 * n; s->d_s[1] = s->d_a + 3 * n; s->d_sc = s->d_a + 4 * n; s->d_part = s->d_a + 6 * n;
+        if (!ctx->h_scratch) e = cudaMallocHost(&ctx->h_scratch, 256);
+        s->h_ip = (fe*)ctx->h_scratch;
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_a, a_mont, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_b, b_mont, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_s[0], &one, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);   // s_0 = (1)
@@ -172,9 +181,7 @@ int zk_ipa_round_lr(zk_ipa* s, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12], u
                 : inner_product<FpParams>(s, s->d_a, s->d_b + h, h, s->d_part + IP_BLOCKS + 1);
     if (rc) return rc;
     ZK_CUDA(cudaMemcpyAsync(s->h_ip, s->d_part + IP_BLOCKS, 2 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = pallas ? ipa_expand_and_msm<FqParams>(s, h, 0, out_l_xyz) : ipa_expand_and_msm<FpParams>(s, h, 0, out_l_xyz);
-    if (rc) return rc;
-    rc = pallas ? ipa_expand_and_msm<FqParams>(s, h, 1, out_r_xyz) : ipa_expand_and_msm<FpParams>(s, h, 1, out_r_xyz);
+    rc = pallas ? ipa_expand_and_msm<FqParams>(s, h, out_l_xyz, out_r_xyz) : ipa_expand_and_msm<FpParams>(s, h, out_l_xyz, out_r_xyz);
     if (rc) return rc;
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(out_ip_l, &s->h_ip[0], 32);

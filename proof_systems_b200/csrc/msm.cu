@@ -459,9 +459,10 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
             ws.cap_bits = need_bits;
         }
         if (ws.cap_hbits < (size_t)G * c) {   // sized by G*c alone: few wide groups and many narrow ones differ
+            if (ws.defer_sync) ZK_CUDA(cudaStreamSynchronize(st));   // an earlier deferred result may still be in flight
             if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
             ws.h_bitsums = nullptr; ws.cap_hbits = 0;
-            ZK_CUDA(cudaMallocHost(&ws.h_bitsums, (size_t)G * c * sizeof(xyzz_t)));
+            ZK_CUDA(cudaMallocHost(&ws.h_bitsums, 2 * (size_t)G * c * sizeof(xyzz_t)));
             ws.cap_hbits = (size_t)G * c;
         }
         if (!ws.d_meta) {
@@ -512,14 +513,15 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     nl += 8;
     STAGE_MARK(6);
     ZK_CUDA(cudaGetLastError());
-    ZK_CUDA(cudaMemcpyAsync(ws.h_bitsums, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaMemcpyAsync(ws.h_bitsums + (size_t)(ws.h_slot & 1) * G * c, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
+    shape->c = c; shape->groups = G;
+    if (launches) *launches += nl;
+    if (ws.defer_sync) return ZK_OK;
     ZK_CUDA(cudaStreamSynchronize(st));
     if (ws.profile)
         for (int k = 0; k < MSM_ST_COUNT; k++) ZK_CUDA(cudaEventElapsedTime(&ws.stage_ms[k], ws.ev[k], ws.ev[k + 1]));
 #undef STAGE_MARK
-    if (launches) *launches += nl;
     // the O(c) serial tail (c doublings per group) is finished on the host from ws.h_bitsums (api.cu: msm_finish)
-    shape->c = c; shape->groups = G;
     return ZK_OK;
 }
 

@@ -49,7 +49,9 @@ struct MsmWorkspace {
     uint32_t* d_task_off = nullptr;   // [G*B + 1] exclusive scan of ceil(count / K)
     xyzz_t* d_buckets = nullptr;      // [G*B]
     xyzz_t* d_bitsums = nullptr;      // [G][c][blocks] then [G][c]
-    xyzz_t* h_bitsums = nullptr;      // pinned host copy of [G][c]
+    xyzz_t* h_bitsums = nullptr;      // pinned host copies of [G][c]: two slots (a lane may run ahead of the host tail by one MSM)
+    unsigned h_slot = 0;              // slot the next msm_run writes (result at h_bitsums + h_slot * G * c)
+    bool defer_sync = false;          // msm_run returns after enqueueing the D2H copy; the caller synchronises
     uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets
     uint32_t* d_giants = nullptr;     // [MSM_MAX_GIANTS] bucket ids
     xyzz_t* d_giant_slices = nullptr; // [MSM_MAX_GIANTS][GIANT_SLICES] per-CTA slice sums of a giant's partials

@@ -182,6 +182,22 @@ int zk_srs_commit_evaluations_non_hiding(zk_srs* srs, size_t domain_size, const 
     return zk_jacobian_to_affine(srs->curve, jac, out_xy);
 }
 
+// k independent commit_evaluations_non_hiding calls on the same domain (the reference issues the 15 witness columns from
+// rayon workers at once, kimchi/src/prover.rs:329-351): evals_mont = k x domain_size, out_xy = k x 8.
+int zk_srs_commit_evaluations_batch(zk_srs* srs, size_t domain_size, const uint64_t* evals_mont, size_t k, uint64_t* out_xy) {
+    if (!srs || (!evals_mont && k) || (!out_xy && k)) { zk_set_error("commit_evaluations_batch: null argument"); return ZK_ERR_INVALID; }
+    auto it = srs->lagrange.find(domain_size);
+    if (it == srs->lagrange.end()) { zk_set_error("commit_evaluations: no Lagrange basis registered for domain size %zu", domain_size); return ZK_ERR_INVALID; }
+    std::vector<uint64_t> jac(12 * k);
+    int rc = zk_msm_batch(srs->ctx, it->second, 0, domain_size, evals_mont, k, /*mont=*/1, 0, jac.data());
+    if (rc) return rc;
+    for (size_t j = 0; j < k; j++) {
+        rc = zk_jacobian_to_affine(srs->curve, jac.data() + 12 * j, out_xy + 8 * j);
+        if (rc) return rc;
+    }
+    return ZK_OK;
+}
+
 int zk_srs_mask_custom(zk_srs* srs, const uint64_t* chunks_xy, size_t n_chunks, const uint64_t* blinders_mont, size_t n_blinders, uint64_t* out_xy) {
     if (!srs || !chunks_xy || !blinders_mont || !out_xy) { zk_set_error("mask_custom: null argument"); return ZK_ERR_INVALID; }
     if (n_chunks != n_blinders) {

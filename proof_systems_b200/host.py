@@ -105,6 +105,16 @@ class SRS:
         check(lib().zk_srs_commit_evaluations_non_hiding(self._h, domain_size, _ptr(e), e.shape[0], out.ctypes.data_as(_u64p)))
         return PolyComm(out)
 
+    def commit_evaluations_non_hiding_batch(self, domain_size: int, evals) -> list:
+        """[commit_evaluations_non_hiding(domain, e) for e in evals] in one call: evals uint64 [k, domain_size, 4].  The
+        reference computes the witness commitments concurrently (kimchi/src/prover.rs:329-351); here the k MSMs share lanes."""
+        e = np.ascontiguousarray(evals, dtype=np.uint64)
+        if e.ndim != 3 or e.shape[1:] != (domain_size, 4):
+            raise ValueError("expected uint64 [k, domain_size, 4]")
+        out = np.zeros((e.shape[0], 8), dtype=np.uint64)
+        check(lib().zk_srs_commit_evaluations_batch(self._h, domain_size, _ptr(e), e.shape[0], out.ctypes.data_as(_u64p)))
+        return [PolyComm(out[j:j + 1]) for j in range(e.shape[0])]
+
     # fn mask_custom(&self, com: PolyComm<G>, blinders: &PolyComm<F>) -> Result<BlindedCommitment<G>, CommitmentError>
     def mask_custom(self, com: PolyComm, blinders) -> PolyComm:
         b = _np_u64(blinders, (4,))

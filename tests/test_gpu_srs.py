@@ -166,3 +166,32 @@ def test_srs_from_file(ctx, orc, vesta_srs, tmp_path):
     assert np.array_equal(fresh.get_lagrange_basis_from_domain_size(n), G.lagrange_small(n))  # built on the device
     srs.close()
     fresh.close()
+
+
+def test_commit_evaluations_batch_and_lanes(ctx, orc, pallas_srs):
+    """15 witness-like columns in one call (kimchi/src/prover.rs:329-351): identical to 15 single calls, for every lane count."""
+    G = pallas_srs
+    n = 2048
+    srs = zk.SRS(ctx, G.cid, G.g[:n], G.mont_points(G.h_xy_canon)[0])
+    srs.add_lagrange_basis(n, G.mont_points(G.lag_2048_canon))
+    ev = orc.to_mont(G.scalar, orc.random_scalars(G.scalar, 15 * n, seed=5)).reshape(15, n, 4)
+    ev[3] = 0
+    ev[4, : n - 5] = orc.to_mont(G.scalar, orc.ints_to_limbs([1]))[0]
+    want = [orc.msm_mont(G.cid, G.mont_points(G.lag_2048_canon), ev[j]) for j in range(15)]
+    try:
+        for lanes in (4, 1, 3):
+            ctx.set_option("msm_lanes", lanes)
+            got = srs.commit_evaluations_non_hiding_batch(n, ev)
+            for j in range(15):
+                assert np.array_equal(got[j].chunks[0], want[j]), (lanes, j)
+        single = srs.commit_evaluations_non_hiding(n, ev[7])
+        assert np.array_equal(single.chunks[0], want[7])
+        # chunked commit_non_hiding (7 chunks of t) goes through the same lanes
+        c7 = srs.commit_non_hiding(ev[:7].reshape(-1, 4), 7)
+        for j in range(7):
+            assert np.array_equal(c7.chunks[j], orc.msm_mont(G.cid, G.g[:n], ev[j]))
+        with pytest.raises(zk.ZkError):
+            ctx.set_option("msm_lanes", 9)
+    finally:
+        ctx.set_option("msm_lanes", 4)
+    srs.close()

@@ -58,7 +58,7 @@ def run_gpu(g, lag, wit_m, dense, big):
     t_setup = time.perf_counter()
     srs = zk.SRS(ctx, CID, g, g[0])
     srs.add_lagrange_basis(N, lag)
-    g_plain = ctx.upload_bases(CID, g, window_bits=0)     # for the IPA rounds (bases change every round in the real prover)
+    g_table = ctx.upload_bases(CID, g)                    # the IPA rounds read the SRS table (the bases are never folded)
     setup = time.perf_counter() - t_setup
     out = {}
 
@@ -74,7 +74,7 @@ def run_gpu(g, lag, wit_m, dense, big):
     p_wit2, p_big4 = pinned(wit_m), pinned(big[: 4 * N])
 
     def once():
-        stage("15 witness commitments", lambda: [srs.commit_evaluations_non_hiding(N, p_wit[k]) for k in range(15)])
+        stage("15 witness commitments", lambda: srs.commit_evaluations_non_hiding_batch(N, p_wit))
         stage("15 iFFT(n)", lambda: ctx.ntt_inplace(FS, p_wit2, inverse=True))
         stage("z: iFFT(n) + MSM", lambda: (ctx.ntt_inplace(FS, p_dense[0], inverse=True), srs.commit_non_hiding(p_dense[0], 1)))
         p_pad[:15, :N] = p_wit
@@ -85,12 +85,15 @@ def run_gpu(g, lag, wit_m, dense, big):
         stage("2 iFFT(n)", lambda: ctx.ntt_inplace(FS, p_dense[:2], inverse=True))
 
         def open_rounds():
+            # the folding loop of SRS::open with a, b resident and the bases taken from the SRS table (csrc/ipa.cu); the
+            # challenges are stand-ins (the sponge is the caller's)
+            rounds = zk.IpaRounds(ctx, g_table, p_dense[0], p_dense[1])
             res = []
             for r in range(LOG_N):
-                m = (N >> (r + 1)) + 2
-                sc = orc_scalars[:m]
-                res.append(ctx.msm(g_plain, sc, off=0))
-                res.append(ctx.msm(g_plain, sc, off=N - m))
+                res.append(rounds.lr())
+                rounds.fold(orc_scalars[2 * r], orc_scalars[2 * r + 1])
+            res.append(rounds.sg())
+            rounds.close()
             return res
         stage("open: 2 x 16 MSMs", open_rounds)
 
