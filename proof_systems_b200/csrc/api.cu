@@ -350,6 +350,18 @@ int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value) {
         ctx->ws.chunk = (uint32_t)value;
         return ZK_OK;
     }
+    if (!strcmp(name, "msm_reduce")) {
+        if (value < 0 || value > 1) { zk_set_error("set_option: msm_reduce %ld outside [0, 1]", value); return ZK_ERR_INVALID; }
+        ctx->ws.reduce_mode = (int)value;
+        for (auto& w : ctx->ws_side) w.reduce_mode = (int)value;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "msm_finish")) {
+        if (value < 0 || value > 2) { zk_set_error("set_option: msm_finish %ld outside [0, 2]", value); return ZK_ERR_INVALID; }
+        ctx->ws.finish_mode = (int)value;
+        for (auto& w : ctx->ws_side) w.finish_mode = (int)value;
+        return ZK_OK;
+    }
     if (!strcmp(name, "msm_lanes")) {
         if (value < 1 || value > 1 + zk_ctx::SIDE_LANES) { zk_set_error("set_option: msm_lanes %ld outside [1, %d]", value, 1 + zk_ctx::SIDE_LANES); return ZK_ERR_INVALID; }
         ctx->lanes = (int)value;

@@ -361,7 +361,58 @@ __global__ void __launch_bounds__(64) k_bitsum_final(const xyzz_t* __restrict__ 
     if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, acc);
 }
 
-// ---------------------------------------------------------------------------------------------- workspace
+// Two-level form of the same reduction (fewer additions, shorter dependency chains).  Split i = hi * W + lo, W = 2^w_lo:
+//     sum_i i * B[i] = W * sum_hi hi * R[hi] + sum_lo lo * C[lo],   R[hi] = sum_lo B[hi W + lo],  C[lo] = sum_hi B[hi W + lo]
+// k_gridsum: one CTA per row and per column of the (B/W + 1) x W bucket grid (row B/W holds the single bucket i = B);
+// k_gridsum_final: one CTA per output bit: T_t = sum of C[lo] over bit t of lo (t < w_lo), of R[hi] over bit t - w_lo of hi
+// (t >= w_lo).  Output layout and meaning are those of k_bitsum_final: c points per group, the MSM is sum_t 2^t T_t.
+// About 2 B additions per group instead of (c - 1) B / 2.
+template <class F>
+__global__ void __launch_bounds__(TREE_THREADS) k_gridsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned w_lo, xyzz_t* rc) {
+    extern __shared__ xyzz_t sm_tree[];
+    const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
+    const unsigned g = blockIdx.z;
+    const xyzz_t* bk = buckets + (size_t)g * B;
+    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
+    const bool row = blockIdx.x < nrows;
+    const uint32_t fixed = row ? blockIdx.x : blockIdx.x - nrows, count = row ? W : nrows;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t e0 = 0; e0 < count; e0 += nq) {
+        const uint32_t e = e0 + qd;
+        xyzz_t o = xyzz_identity();
+        if (e < count) {
+            const uint32_t i = row ? fixed * W + e : e * W + fixed;
+            if (i >= 1 && i <= B) o = load_xyzz(bk + (i - 1));
+        }
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
+    if (threadIdx.x == 0) store_xyzz(rc + (size_t)g * (nrows + W) + blockIdx.x, acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(TREE_THREADS) k_gridsum_final(const xyzz_t* __restrict__ rc, uint32_t B, unsigned w_lo, unsigned c, xyzz_t* out) {
+    extern __shared__ xyzz_t sm_tree[];
+    const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
+    const unsigned t = blockIdx.x, g = blockIdx.y;
+    const bool cols = t < w_lo;
+    const xyzz_t* src = rc + (size_t)g * (nrows + W) + (cols ? nrows : 0);
+    const uint32_t count = cols ? W : nrows;
+    const unsigned bit = cols ? t : t - w_lo;
+    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
+    xyzz_t acc = xyzz_identity();
+    // the j-th index with `bit` set: e = (j >> bit) << (bit + 1) | 1 << bit | (j & (2^bit - 1))
+    for (uint32_t j0 = 0;; j0 += nq) {
+        const uint32_t first = ((j0 >> bit) << (bit + 1)) | (1u << bit) | (j0 & ((1u << bit) - 1));
+        if (first >= count) break;     // uniform over the block
+        const uint32_t j = j0 + qd, e = ((j >> bit) << (bit + 1)) | (1u << bit) | (j & ((1u << bit) - 1));
+        xyzz_t o = e < count ? load_xyzz(src + e) : xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)g * c + t, acc);
+}
+
 // ---------------------------------------------------------------------------------------------- workspace
 static void free_dev(void* p) { if (p) cudaFree(p); }
 
@@ -400,14 +451,15 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     // <= 128 registers); K is chosen so that the tasks fill a whole number of waves (a 1.02-wave grid costs two waves).
     const size_t capacity = (size_t)ws.sm_count * 512;
     const size_t resident_quads = (size_t)ws.sm_count * TREE_QUADS;
-    const bool serial_finish = NB > resident_quads;   // many small buckets: throughput regime (see k_bucket_finish_serial)
+    const bool many_buckets = NB > resident_quads;    // many small buckets: throughput regime (see k_bucket_finish_serial)
+    const bool serial_finish = ws.finish_mode == 0 ? many_buckets : ws.finish_mode == 1;
     uint32_t K = ws.chunk;
     if (K == 0) {
         const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
         size_t waves = (Mmax + 64 * capacity - 1) / (64 * capacity);   // long tasks for large inputs: fewer partials to sum
         if (waves == 0) waves = 1;
         // a cheap finish pass affords twice as many (half as long, better balanced) tasks
-        if (serial_finish && Mmax / (2 * waves * capacity) >= 6) waves *= 2;
+        if (many_buckets && Mmax / (2 * waves * capacity) >= 6) waves *= 2;
         K = (uint32_t)((Mmax + waves * capacity - slack - 1) / (waves * capacity - slack));
         if (K < 4) K = 4;
     }
@@ -451,7 +503,9 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
             ZK_CUDA(cudaMalloc(&ws.d_buckets, NB * sizeof(xyzz_t)));
             ws.cap_buckets = NB;
         }
-        const size_t need_bits = (size_t)G * c * (nblk + 1);
+        const unsigned w_lo = (c - 1) / 2;
+        const size_t grid_pts = (size_t)G * (((size_t)B >> w_lo) + 1 + ((size_t)1 << w_lo));
+        const size_t need_bits = std::max((size_t)G * c * (nblk + 1), grid_pts + (size_t)G * c);
         if (ws.cap_bits < need_bits) {
             free_dev(ws.d_bitsums);
             ws.d_bitsums = nullptr; ws.cap_bits = 0;
@@ -506,10 +560,25 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     STAGE_MARK(5);
     // 6. bit-sliced bucket sums
     xyzz_t* d_partial = ws.d_bitsums;
-    xyzz_t* d_T = ws.d_bitsums + (size_t)G * c * nblk;
-    if (c > 1 && B >= 2)
-        k_bitsum<F><<<dim3(nblk, c - 1, G), bs_threads, (bs_threads / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, c, d_partial);
-    k_bitsum_final<F><<<G * c, 64, 16 * sizeof(xyzz_t), st>>>(d_partial, ws.d_buckets, B, c, nblk, d_T);
+    xyzz_t* d_T;
+    if (ws.reduce_mode == 0) {
+        d_T = ws.d_bitsums + (size_t)G * c * nblk;
+        if (c > 1 && B >= 2)
+            k_bitsum<F><<<dim3(nblk, c - 1, G), bs_threads, (bs_threads / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, c, d_partial);
+        k_bitsum_final<F><<<G * c, 64, 16 * sizeof(xyzz_t), st>>>(d_partial, ws.d_buckets, B, c, nblk, d_T);
+    } else {
+        const unsigned w_lo = (c - 1) / 2;
+        const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
+        d_T = ws.d_bitsums + (size_t)G * (nrows + W);
+        // a quad per 1-2 elements of a row / column, but never more CTAs x threads than are resident at once (the kernels
+        // need ~190 registers: 320 threads per SM), so that the whole grid runs as one wave
+        unsigned gt = TREE_THREADS;
+        while (gt > 32 && (gt / 4 >= 2 * std::max(W, nrows) || (size_t)G * (nrows + W) * gt > (size_t)ws.sm_count * 320)) gt /= 2;
+        k_gridsum<F><<<dim3(nrows + W, 1, G), gt, (gt / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, w_lo, d_partial);
+        unsigned ft = TREE_THREADS;                 // half of the elements carry a given bit
+        while (ft > 32 && ft / 4 >= std::max(W, nrows)) ft /= 2;
+        k_gridsum_final<F><<<dim3(c, G), ft, (ft / 4) * sizeof(xyzz_t), st>>>(d_partial, B, w_lo, c, d_T);
+    }
     nl += 8;
     STAGE_MARK(6);
     ZK_CUDA(cudaGetLastError());

@@ -8,6 +8,10 @@ sys.path.insert(0, ROOT)
 import proof_systems_b200 as zk
 from bench import splitmix64_limbs
 ctx = zk.Context(0)
+if os.environ.get("MSM_REDUCE"): ctx.set_option("msm_reduce", int(os.environ["MSM_REDUCE"]))
+if os.environ.get("MSM_CHUNK"): ctx.set_option("msm_chunk", int(os.environ["MSM_CHUNK"]))
+if os.environ.get("MSM_FINISH"): ctx.set_option("msm_finish", int(os.environ["MSM_FINISH"]))
+KS = [int(x) for x in os.environ.get("MSM_LOGS", "8,10,11,12,13,14,15,16").split(",")]
 stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 z = np.load(os.path.join(ROOT, "tests", "golden", "pallas_srs.npz"))
@@ -20,7 +24,7 @@ def timed(fn, reps=7):
         e0.record(stream); fn(); e1.record(stream); e1.synchronize(); ts.append(e0.elapsed_time(e1))
     return float(np.median(ts[2:]))
 rows = []
-for k in (8, 10, 11, 12, 13, 14, 15, 16):
+for k in KS:
     n = 1 << k
     bases = ctx.upload_bases(zk.PALLAS, g[:n])
     for kind in ("uniform", "ones"):
