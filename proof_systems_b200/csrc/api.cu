@@ -557,16 +557,61 @@ int zk_ntt_batch(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, size
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));
     if (batch == 0) return ZK_OK;
-    size_t bytes = ((size_t)batch << log_n) * sizeof(fe);
+    const size_t n = (size_t)1 << log_n, poly_bytes = n * sizeof(fe), bytes = batch * poly_bytes;
+    if (in_len == 0 || in_len > n || inverse) in_len = n;
     // (Transforming page-locked memory in place over PCIe was measured and is slower than two staged copies: the tile loads
     //  are 64-128 B requests.  MSM scalars, read once in full lines, do take the zero-copy route — zk_msm_batch.)
     int rc = ctx_ensure((void**)&ctx->d_ntt, &ctx->cap_ntt, bytes);
     if (rc) return rc;
-    ZK_CUDA(cudaMemcpyAsync(ctx->d_ntt, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = ctx_ntt_device(ctx, field_id, ctx->d_ntt, log_n, batch, in_len, inverse, coset);
+    // Only the first in_len coefficients of every polynomial cross PCIe (the kernels zero-pad by position), and for batches in
+    // page-locked memory the three stages are pipelined over chunks of polynomials: copy-in of chunk k+1, the transform of
+    // chunk k and the copy-out of chunk k-1 run on three streams.  16 x FFT(8n) of kimchi's quotient step (in_len = n) moves
+    // 32 MiB in and 256 MiB out: the call is bound by the copy-out alone instead of the sum of all three.
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, data) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    size_t per = batch;                                  // polynomials per chunk
+    if (pinned && !ctx->profile && batch >= 2 && bytes >= ((size_t)8 << 20)) {
+        per = std::max<size_t>(1, ((size_t)16 << 20) / poly_bytes);
+        if (per * 2 > batch) per = (batch + 1) / 2;
+    }
+    if (per == batch) {
+        ZK_CUDA(cudaMemcpy2DAsync(ctx->d_ntt, poly_bytes, data, poly_bytes, in_len * sizeof(fe), batch, cudaMemcpyHostToDevice, ctx->stream));
+        rc = ctx_ntt_device(ctx, field_id, ctx->d_ntt, log_n, batch, in_len, inverse, coset);
+        if (rc) return rc;
+        ZK_CUDA(cudaMemcpyAsync(data, ctx->d_ntt, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return ZK_OK;
+    }
+    rc = ctx_lanes_init(ctx);
     if (rc) return rc;
-    ZK_CUDA(cudaMemcpyAsync(data, ctx->d_ntt, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaStream_t s_in = ctx->side[0], s_out = ctx->side[1];
+    const size_t chunks = (batch + per - 1) / per;
+    std::vector<cudaEvent_t> ev(2 * chunks, nullptr);
+    cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);      // work already queued on the caller's stream comes first
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_in, ctx->ev_fork, 0);
+    for (size_t k = 0; k < chunks && e == cudaSuccess && rc == ZK_OK; k++) {
+        const size_t j0 = k * per, cnt = std::min(per, batch - j0);
+        fe* d = ctx->d_ntt + j0 * n;
+        const uint64_t* h = data + 4 * j0 * n;
+        e = cudaEventCreateWithFlags(&ev[2 * k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[2 * k + 1], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(d, poly_bytes, h, poly_bytes, in_len * sizeof(fe), cnt, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[2 * k], s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[2 * k], 0);
+        if (e != cudaSuccess) break;
+        rc = ctx_ntt_device(ctx, field_id, d, log_n, cnt, in_len, inverse, coset);
+        if (rc) break;
+        e = cudaEventRecord(ev[2 * k + 1], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, ev[2 * k + 1], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((void*)h, d, cnt * poly_bytes, cudaMemcpyDeviceToHost, s_out);
+    }
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(s_out);
+    for (auto& x : ev) if (x) cudaEventDestroy(x);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) { zk_set_error("ntt: %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); return ZK_ERR_CUDA; }
     return ZK_OK;
 }
 
