@@ -109,36 +109,43 @@ def run_gpu(g, lag, wit_m, dense, big):
 
 def run_cpu(g, lag, wit_m, dense, big):
     th = orc.host_threads()
-    out = {}
+    out, used = {}, {}
+    cands = sorted({t for t in (1, 8, 32, th) if t <= th})
 
     def stage(name, fn):
-        t0 = time.perf_counter()
-        fn()
-        out[name] = time.perf_counter() - t0
+        """every stage gets its best thread count (the oracle's OpenMP loops do not scale to 128 threads on small inputs)"""
+        best = None
+        for t in cands:
+            t0 = time.perf_counter()
+            fn(t)
+            el = time.perf_counter() - t0
+            if best is None or el < best:
+                best, used[name] = el, t
+        out[name] = best
 
     sc = orc.random_scalars(FS, N, seed=8)
-    t0 = time.perf_counter()
-    stage("15 witness commitments", lambda: [orc.msm_mont(CID, lag, wit_m[k], threads=th) for k in range(15)])
-    stage("15 iFFT(n)", lambda: [orc.ntt(FS, wit_m[k], inverse=True, threads=th) for k in range(15)])
-    stage("z: iFFT(n) + MSM", lambda: (orc.ntt(FS, dense[0], inverse=True, threads=th), orc.msm_split2(CID, g, orc.from_mont(FS, dense[0]), threads=th)))
+    stage("15 witness commitments", lambda t: [orc.msm_mont(CID, lag, wit_m[k], threads=t) for k in range(15)])
+    stage("15 iFFT(n)", lambda t: [orc.ntt(FS, wit_m[k], inverse=True, threads=t) for k in range(15)])
+    stage("z: iFFT(n) + MSM", lambda t: (orc.ntt(FS, dense[0], inverse=True, threads=t), orc.msm_split2(CID, g, orc.from_mont(FS, dense[0]), threads=t)))
 
-    def fft8():
+    def fft8(t):
         for k in range(16):
             pad = np.zeros((8 * N, 4), dtype=np.uint64)
             pad[:N] = wit_m[k] if k < 15 else dense[0]
-            orc.ntt(FS, pad, threads=th)
+            orc.ntt(FS, pad, threads=t)
     stage("16 FFT(8n)", fft8)
-    stage("iFFT(4n) + iFFT(8n)", lambda: (orc.ntt(FS, big[: 4 * N], inverse=True, threads=th), orc.ntt(FS, big, inverse=True, threads=th)))
-    stage("t: 7 MSMs", lambda: [orc.msm_mont(CID, g, dense[1 + k], threads=th) for k in range(7)])
-    stage("2 iFFT(n)", lambda: [orc.ntt(FS, dense[k], inverse=True, threads=th) for k in range(2)])
+    stage("iFFT(4n) + iFFT(8n)", lambda t: (orc.ntt(FS, big[: 4 * N], inverse=True, threads=t), orc.ntt(FS, big, inverse=True, threads=t)))
+    stage("t: 7 MSMs", lambda t: [orc.msm_mont(CID, g, dense[1 + k], threads=t) for k in range(7)])
+    stage("2 iFFT(n)", lambda t: [orc.ntt(FS, dense[k], inverse=True, threads=t) for k in range(2)])
 
-    def open_rounds():
+    def open_rounds(t):
         for r in range(LOG_N):
             m = (N >> (r + 1)) + 2
-            orc.msm(CID, g[:m], sc[:m], threads=th)
-            orc.msm(CID, g[N - m:], sc[:m], threads=th)
-    stage("open: 2 x 16 MSMs", open_rounds)
-    return {"total_s": time.perf_counter() - t0, "stages_s": out, "threads": th}
+            orc.msm(CID, g[:m], sc[:m], threads=t)
+            orc.msm(CID, g[N - m:], sc[:m], threads=t)
+    stage("open: 2 x 16 MSMs (no base folding counted)", open_rounds)
+    return {"total_s": sum(out.values()), "stages_s": out, "threads_per_stage": used, "host_threads": th}
+
 
 
 if __name__ == "__main__":

@@ -44,7 +44,7 @@ if os.path.exists(os.path.join(G, "launches.csv")):
         idx = [i for i, o in enumerate(order) if "k_recode" in o[0]]
         if idx:
             i0 = idx[-1]
-            i1 = next((i for i in range(i0 + 1, len(order)) if "k_bitsum_final" in order[i][0] or "k_finish" in order[i][0]), len(order) - 1)
+            i1 = next((i for i in range(i0 + 1, len(order)) if "k_gridsum_final" in order[i][0] or "k_bitsum_final" in order[i][0] or "k_finish" in order[i][0]), len(order) - 1)
             for o in order[i0:i1 + 1]:
                 f.write(f"| `{o[0][:70]}` | {o[1]} | {o[2]} | {o[3] / 1e3:.1f} |\n")
     print("wrote", f"{tag}_launches.md")
