@@ -11,7 +11,8 @@ followed by one 2^16-element Fp NTT.  The headline metric is the MSM's points/s;
   e2e    : the same step through the host-pointer C-ABI calls (zk_msm / zk_ntt_batch): scalars and polynomial start in
            PINNED host memory, H2D and D2H inside the timed region
 N > 1 (weak scaling): every rank holds the SRS and runs its own 2^16-point slice of an (N * 2^16)-point MSM; the N
-Jacobian partials (96 B each) are exchanged with one NCCL all_gather and summed.  NTT: N independent replicas.
+partials stay on the device as c slice sums (128 B each), are exchanged with one NCCL all_gather enqueued behind the kernels and
+summed on the device (proof_systems_b200/parallel.py: ShardedMsm).  NTT: N independent replicas.
 Between timed iterations a 256 MiB buffer is overwritten to flush the 126 MB L2.
 """
 import argparse
@@ -222,21 +223,24 @@ def main():
     def flush_l2():
         flush.fill_(rank + 1)
 
-    from proof_systems_b200.parallel import PointSumAllGather
+    from proof_systems_b200.parallel import ShardedMsm
 
-    # final point-sum: one NCCL all_gather of the 96-byte Jacobian partials, then N-1 additions on every rank
-    reduce_partials = PointSumAllGather(zk.PALLAS, torch.device("cuda", local))
+    # N > 1: the slice sums stay on the device, one NCCL all_gather of N x c x 128 bytes rides the context's stream behind the
+    # kernels, the partials are added on the device and read back once (proof_systems_b200/parallel.py)
+    sharded = ShardedMsm(ctx, zk.PALLAS, torch.device("cuda", local), stream) if world > 1 else None
 
     def step_resident():
-        jac = ctx.msm_dev(bases, d_scalars.data_ptr(), N_PTS)
-        return reduce_partials(jac)
+        if sharded:
+            return sharded(bases, d_scalars.data_ptr(), N_PTS)
+        return ctx.msm_dev(bases, d_scalars.data_ptr(), N_PTS)
 
     def ntt_resident():
         ctx.ntt_dev(zk.FP, d_poly.data_ptr(), LOG_N)
 
     def step_e2e():
-        jac = ctx_msm_host()
-        return reduce_partials(jac)
+        if sharded:
+            return sharded(bases, h_scalars.data_ptr(), N_PTS)   # page-locked scalars are read over PCIe by the first kernel
+        return ctx_msm_host()
 
     import ctypes
 
@@ -356,11 +360,11 @@ def main():
         "dtype": "u256 (8 x u32 Montgomery limbs)", "data": "synthetic",
         "config": {
             "workload": "2^16-point Pallas MSM on the reference's srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)"
-                        + ("" if world == 1 else f"; rank r adds its own 2^16-scalar slice: one {world * N_PTS}-point MSM, all_gather of 96 B partials"),
+                        + ("" if world == 1 else f"; rank r adds its own 2^16-scalar slice: one {world * N_PTS}-point MSM, all_gather of {wb} x 128 B slice sums"),
             "window_bits": wb, "resident_table_mib": round(len(bases) * 64 * ((256 + wb - 1) // wb if wb else 1) / 2**20, 1),
             "l2": "256 MiB buffer overwritten between timed iterations (flush)", "result_matches_cpu_oracle": ok,
         },
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": N_PTS * 32, "d2h_bytes_per_step": 96 + 128 * max(wb, 1),
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": N_PTS * 32, "d2h_bytes_per_step": 128 * max(wb, 1),
                 "ms_per_step": msm_e2e_ms / args.steps},
         "gpu_launches": int(launches_total),
         "clocks": clocks,

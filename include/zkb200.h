@@ -104,6 +104,19 @@ int zk_msm_dev(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const v
 /* k MSMs sharing the same bases slice (the chunks of t, the 15 witness columns): scalars k x n x 4, out k x 12. */
 int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, size_t k,
                  int scalars_are_mont, int window_bits, uint64_t* out_xyz);
+
+/* Multi-GPU sharding by points (the reference's own split is poly-commitment/src/ipa.rs:652-662 and
+ * benches/msm.rs:92-140).  zk_msm_partial runs this rank's slice and leaves its result on the DEVICE as groups*c "slice sums"
+ * (XYZZ points, 128 bytes each; the MSM is sum_g 2^(c g) sum_t 2^t T[g][t]) in d_out — nothing is copied to the host and
+ * nothing is synchronised, so the caller enqueues the all-gather of d_out (ncclAllGather, world x groups*c x 128 bytes) on the
+ * context's stream while the kernels still run.  zk_msm_finish_gathered adds the gathered partials slice by slice on the
+ * device, reads groups*c points back and finishes the O(c) tail on the host; every rank gets identical bits.  `scalars` may
+ * be device memory, page-locked host memory (read over PCIe) or pageable host memory (staged).  All ranks must use bases with
+ * the same window (same c and groups). */
+int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* scalars, int scalars_are_mont,
+                   int window_bits, void* d_out, size_t capacity_points, unsigned* out_c, unsigned* out_groups);
+int zk_msm_finish_gathered(zk_ctx* ctx, int curve_id, const void* d_all, size_t world, unsigned c, unsigned groups,
+                           uint64_t out_xyz[12]);
 /* Projective::into_affine / `+` on the host (result handling; multi-GPU partial sums after the all-gather). */
 int zk_jacobian_to_affine(int curve_id, const uint64_t xyz[12], uint64_t out_xy[8]);
 int zk_jacobian_add(int curve_id, const uint64_t a_xyz[12], const uint64_t b_xyz[12], uint64_t out_xyz[12]);

@@ -63,6 +63,8 @@ def lib() -> ctypes.CDLL:
     L.zk_msm.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
     L.zk_msm_dev.argtypes = [vp, vp, sz, sz, vp, i, i, _u64p]
     L.zk_msm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i, i, _u64p]
+    L.zk_msm_partial.argtypes = [vp, vp, sz, sz, vp, i, i, vp, sz, ctypes.POINTER(u), ctypes.POINTER(u)]
+    L.zk_msm_finish_gathered.argtypes = [vp, i, vp, sz, u, u, _u64p]
     L.zk_jacobian_to_affine.argtypes = [i, _u64p, _u64p]
     L.zk_jacobian_add.argtypes = [i, _u64p, _u64p, _u64p]
     L.zk_jacobian_sum.argtypes = [i, _u64p, sz, _u64p]
@@ -206,6 +208,19 @@ class Context:
     def msm_dev(self, bases: "Bases", d_scalars: int, n: int, off: int = 0, mont: bool = False, window_bits: int = 0) -> np.ndarray:
         out = _out(12)
         check(lib().zk_msm_dev(self._h, bases._h, off, n, ctypes.c_void_p(d_scalars), int(mont), window_bits, out.ctypes.data_as(_u64p)))
+        return out
+
+    def msm_partial(self, bases: "Bases", scalars_ptr: int, n: int, d_out: int, capacity_points: int, off: int = 0, mont: bool = False,
+                    window_bits: int = 0) -> tuple:
+        """This rank's slice of a sharded MSM, left on the device (zk_msm_partial): returns (c, groups); nothing is synchronised."""
+        c, g = ctypes.c_uint(), ctypes.c_uint()
+        check(lib().zk_msm_partial(self._h, bases._h, off, n, ctypes.c_void_p(scalars_ptr), int(mont), window_bits, ctypes.c_void_p(d_out),
+                                   capacity_points, ctypes.byref(c), ctypes.byref(g)))
+        return c.value, g.value
+
+    def msm_finish_gathered(self, curve: int, d_all: int, world: int, c: int, groups: int) -> np.ndarray:
+        out = _out(12)
+        check(lib().zk_msm_finish_gathered(self._h, curve, ctypes.c_void_p(d_all), world, c, groups, out.ctypes.data_as(_u64p)))
         return out
 
     def msm_batch(self, bases: "Bases", scalars, off: int = 0, mont: bool = False, window_bits: int = 0) -> np.ndarray:

@@ -315,6 +315,8 @@ void zk_ctx_destroy(zk_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto& le : ctx->ev_lane) for (auto& e : le) if (e) cudaEventDestroy(e);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+    if (ctx->d_gather_sum) cudaFree(ctx->d_gather_sum);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->d_ntt) cudaFree(ctx->d_ntt);
     if (ctx->d_ntt_tmp) cudaFree(ctx->d_ntt_tmp);
@@ -499,6 +501,73 @@ int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const
     std::vector<const fe*> scs(k);
     for (size_t j = 0; j < k; j++) scs[j] = d_sc + j * n;
     return ctx_msm_many(ctx, bases, offs.data(), n, scs.data(), k, scalars_are_mont, window_bits, out_xyz);
+}
+
+// Multi-GPU sharding: this rank's MSM is left on the device as its slice sums and nothing is synchronised, so
+// the caller can enqueue the all-gather on the same stream while the kernels still run.
+int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* scalars, int scalars_are_mont, int window_bits,
+                   void* d_out, size_t capacity_points, unsigned* out_c, unsigned* out_groups) {
+    if (!ctx || !bases || !d_out || !out_c || !out_groups || (!scalars && n)) { zk_set_error("msm_partial: null argument"); return ZK_ERR_INVALID; }
+    if (bases->ctx != ctx) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
+    if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
+    if (n == 0) { zk_set_error("msm_partial: empty slice"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    const fe* d_sc = nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, scalars) == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+        d_sc = (const fe*)scalars;
+    } else if (attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+        d_sc = (const fe*)attr.devicePointer;          // page-locked: read over PCIe by the recode kernel
+    } else {
+        cudaGetLastError();
+        int rc = ctx_ensure((void**)&ctx->d_scalars, &ctx->cap_scalars, n * sizeof(fe));
+        if (rc) return rc;
+        ZK_CUDA(cudaMemcpyAsync(ctx->d_scalars, scalars, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+        d_sc = ctx->d_scalars;
+    }
+    MsmResultShape shape;
+    unsigned nl = 0;
+    ctx->ws.d_T_out = (xyzz_t*)d_out;
+    ctx->ws.d_T_cap = capacity_points;
+    int rc = bases->b.curve == ZK_PALLAS
+                 ? msm_run<FpParams, FqParams>(bases->b, off, n, d_sc, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl)
+                 : msm_run<FqParams, FpParams>(bases->b, off, n, d_sc, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
+    ctx->ws.d_T_out = nullptr;
+    ctx->ws.d_T_cap = 0;
+    ctx->launches += nl;
+    if (rc) return rc;
+    *out_c = shape.c;
+    *out_groups = shape.groups;
+    return ZK_OK;
+}
+
+// d_all: `world` gathered partials of zk_msm_partial (device, world x groups*c points, same shape on every rank).  Sums them
+// per slice on the device, copies groups*c points to the host and finishes the O(c) tail there.
+int zk_msm_finish_gathered(zk_ctx* ctx, int curve_id, const void* d_all, size_t world, unsigned c, unsigned groups, uint64_t out_xyz[12]) {
+    if (!ctx || !d_all || !out_xyz || world == 0) { zk_set_error("msm_finish_gathered: null argument"); return ZK_ERR_INVALID; }
+    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("msm_finish_gathered: unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
+    const size_t count = (size_t)c * groups;
+    if (count == 0 || count > 4096) { zk_set_error("msm_finish_gathered: bad shape c = %u, groups = %u", c, groups); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx_ensure((void**)&ctx->d_gather_sum, &ctx->cap_gather_sum, count * sizeof(xyzz_t));
+    if (rc) return rc;
+    if (ctx->cap_h_gather < count) {
+        if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+        ctx->h_gather = nullptr; ctx->cap_h_gather = 0;
+        ZK_CUDA(cudaMallocHost(&ctx->h_gather, count * sizeof(xyzz_t)));
+        ctx->cap_h_gather = count;
+    }
+    rc = curve_id == ZK_PALLAS ? msm_sum_partials<FpParams>((const xyzz_t*)d_all, world, count, ctx->d_gather_sum, ctx->stream)
+                               : msm_sum_partials<FqParams>((const xyzz_t*)d_all, world, count, ctx->d_gather_sum, ctx->stream);
+    if (rc) return rc;
+    ctx->launches += 1;
+    ZK_CUDA(cudaMemcpyAsync(ctx->h_gather, ctx->d_gather_sum, count * sizeof(xyzz_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    host::hxyzz r = curve_id == ZK_PALLAS ? msm_finish_t<host::HFp>(ctx->h_gather, c, groups) : msm_finish_t<host::HFq>(ctx->h_gather, c, groups);
+    xyzz_to_jac_out(curve_id, r, out_xyz);
+    return ZK_OK;
 }
 
 int zk_msm(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, int scalars_are_mont, int window_bits, uint64_t out_xyz[12]) {

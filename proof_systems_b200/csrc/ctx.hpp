@@ -24,6 +24,10 @@ struct zk_ctx {
     size_t cap_ntt_tmp = 0;
     zkb::fe* ntt_small[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [field][inverse] w_1024^(+-i)
     std::map<unsigned, zkb::NttTables> ntt_tables;                         // key: field | inverse << 1 | log_n << 2
+    zkb::xyzz_t* d_gather_sum = nullptr; // zk_msm_finish_gathered: cross-rank sums of the slice sums
+    size_t cap_gather_sum = 0;
+    zkb::xyzz_t* h_gather = nullptr;     // ... and their pinned host copy
+    size_t cap_h_gather = 0;
     void* h_scratch = nullptr;           // 256 pinned bytes for small read-backs
     uint64_t launches = 0;
     bool profile = false;                // per-stage device timing (zk_ctx_set_profile)

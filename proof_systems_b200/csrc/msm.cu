@@ -582,6 +582,13 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     nl += 8;
     STAGE_MARK(6);
     ZK_CUDA(cudaGetLastError());
+    if (ws.d_T_out) {
+        if ((size_t)G * c > ws.d_T_cap) { zk_set_error("msm: %u slice sums do not fit the caller's buffer of %zu points", G * c, ws.d_T_cap); return ZK_ERR_INVALID; }
+        ZK_CUDA(cudaMemcpyAsync(ws.d_T_out, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToDevice, st));
+        shape->c = c; shape->groups = G;
+        if (launches) *launches += nl;
+        return ZK_OK;
+    }
     ZK_CUDA(cudaMemcpyAsync(ws.h_bitsums + (size_t)(ws.h_slot & 1) * G * c, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     shape->c = c; shape->groups = G;
     if (launches) *launches += nl;
@@ -593,6 +600,31 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     // the O(c) serial tail (c doublings per group) is finished on the host from ws.h_bitsums (api.cu: msm_finish)
     return ZK_OK;
 }
+
+// one warp per output point: its 8 quads stride over the ranks, then a shuffle tree
+template <class F> __global__ void __launch_bounds__(32) k_sum_partials(const xyzz_t* __restrict__ all, uint32_t world, uint32_t count, xyzz_t* out) {
+    const unsigned i = blockIdx.x, qd = threadIdx.x >> 2;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t r0 = 0; r0 < world; r0 += 8) {
+        const uint32_t r = r0 + qd;
+        xyzz_t o = r < world ? load_xyzz(all + (size_t)r * count + i) : xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+#pragma unroll 1
+    for (unsigned d = 4; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
+        if (qd >= d) o = xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    if (threadIdx.x == 0) store_xyzz(out + i, acc);
+}
+template <class F> int msm_sum_partials(const xyzz_t* d_all, size_t world, size_t count, xyzz_t* d_out, cudaStream_t st) {
+    if (count) k_sum_partials<F><<<(unsigned)count, 32, 0, st>>>(d_all, (uint32_t)world, (uint32_t)count, d_out);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+template int msm_sum_partials<FpParams>(const xyzz_t*, size_t, size_t, xyzz_t*, cudaStream_t);
+template int msm_sum_partials<FqParams>(const xyzz_t*, size_t, size_t, xyzz_t*, cudaStream_t);
 
 #define INST(F, FS)                                                                                                             \
     template int msm_bases_create<F>(MsmBases&, const affine_t*, bool, size_t, unsigned, cudaStream_t);                          \

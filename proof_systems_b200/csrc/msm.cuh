@@ -51,6 +51,8 @@ struct MsmWorkspace {
     xyzz_t* d_bitsums = nullptr;      // [G][c][blocks] then [G][c]
     xyzz_t* h_bitsums = nullptr;      // pinned host copies of [G][c]: two slots (a lane may run ahead of the host tail by one MSM)
     unsigned h_slot = 0;              // slot the next msm_run writes (result at h_bitsums + h_slot * G * c)
+    xyzz_t* d_T_out = nullptr;        // when set: the slice sums are copied HERE (device, capacity d_T_cap points) instead of to
+    size_t d_T_cap = 0;               // the host, and nothing is synchronised (multi-GPU exchange, zk_msm_partial)
     bool defer_sync = false;          // msm_run returns after enqueueing the D2H copy; the caller synchronises
     uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets
     uint32_t* d_giants = nullptr;     // [MSM_MAX_GIANTS] bucket ids
@@ -83,6 +85,9 @@ struct MsmResultShape {
 
 // One MSM over bases[off .. off+n).  d_scalars_in: n scalars already on the device (8 u32 each).  window c: 0 = default
 // (ignored when the bases carry a precomputed table).  Synchronises the stream; the O(c) tail is finished by the caller.
+// out[i] = sum over r < world of all[r * count + i]   (the cross-rank sum of gathered slice sums, i < count)
+template <class F> int msm_sum_partials(const xyzz_t* d_all, size_t world, size_t count, xyzz_t* d_out, cudaStream_t st);
+
 template <class F, class FS>
 int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, bool scalars_mont, unsigned c, MsmWorkspace& ws,
             cudaStream_t st, MsmResultShape* shape, unsigned* launches);

@@ -46,6 +46,36 @@ class PointSumAllGather:
         return jacobian_sum(self.curve, self.h_all.numpy().view(np.uint64))
 
 
+class ShardedMsm:
+    """One MSM sharded by points over the ranks of a process group with the exchange kept on the device: every rank leaves the
+    slice sums of its part in HBM (zk_msm_partial, nothing synchronised), ONE NCCL all_gather of world x c x 128 bytes is
+    enqueued behind the kernels on the context's stream, and the gathered partials are added per slice on the device before
+    the single read-back (zk_msm_finish_gathered).  No host round trip between the MSM and the collective.
+
+    `stream` is the torch stream the context runs on (ctx.set_stream(stream.cuda_stream))."""
+
+    MAX_POINTS = 4096
+
+    def __init__(self, ctx, curve: int, device: torch.device, stream: "torch.cuda.Stream", group=None):
+        self.ctx, self.curve, self.device, self.stream, self.group = ctx, curve, device, stream, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.d_mine = torch.empty((self.MAX_POINTS, 16), dtype=torch.int64, device=device)   # written by the library's stream only
+        self.d_all = None
+
+    def __call__(self, bases, scalars_ptr: int, n: int, off: int = 0, mont: bool = False, window_bits: int = 0) -> np.ndarray:
+        """Every rank must end with the same (c, groups): bases with the same table window, or — without a table — an explicit
+        window_bits (the default window depends on the slice length)."""
+        c, groups = self.ctx.msm_partial(bases, scalars_ptr, n, self.d_mine.data_ptr(), self.MAX_POINTS, off=off, mont=mont, window_bits=window_bits)
+        cnt = c * groups
+        if self.world == 1:
+            return self.ctx.msm_finish_gathered(self.curve, self.d_mine.data_ptr(), 1, c, groups)
+        if self.d_all is None or self.d_all.shape[1] != cnt:
+            self.d_all = torch.empty((self.world, cnt, 16), dtype=torch.int64, device=self.device)
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.d_all, self.d_mine[:cnt], group=self.group)
+        return self.ctx.msm_finish_gathered(self.curve, self.d_all.data_ptr(), self.world, c, groups)
+
+
 def all_gather_point_sum(curve: int, partial_xyz: np.ndarray, group=None, device: torch.device | None = None) -> np.ndarray:
     """Sum the per-rank Jacobian partials.  Works on any backend: pass device=cuda for NCCL, leave None for gloo."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -246,3 +246,36 @@ def test_error_codes(ctx, orc, pallas_srs):
         other.msm(bases, sc)                           # bases belong to another context
     other.close()
     bases.free()
+
+
+def test_partial_and_finish_gathered_emulate_two_ranks(ctx, orc, vesta_srs):
+    """The multi-GPU exchange without the collective: two zk_msm_partial calls on the two halves of the points
+    write their slice sums next to each other — exactly what an all_gather over two ranks produces — and
+    zk_msm_finish_gathered(world = 2) must return the MSM over all points; world = 1 must equal zk_msm."""
+    import torch
+    srs = vesta_srs
+    n = 2048
+    sc = orc.random_scalars(srs.scalar, n, seed=41)
+    want = orc.msm(srs.cid, srs.g[:n], sc)
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    h_sc = torch.from_numpy(sc.view(np.int64).copy()).pin_memory()
+    for wb in (-1, 0):
+        bases = ctx.upload_bases(srs.cid, srs.g[:n], window_bits=wb)
+        d_all = torch.zeros((2, 4096, 16), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()       # torch fills on ITS stream; the context runs on its own
+        w = 0 if wb else 7             # without a table the default window depends on the slice length: ranks must agree on one
+        c, g = ctx.msm_partial(bases, d_sc.data_ptr(), n, d_all.data_ptr(), 4096, window_bits=w)
+        one = ctx.msm_finish_gathered(srs.cid, d_all.data_ptr(), 1, c, g)
+        assert np.array_equal(zk.jacobian_to_affine(srs.cid, one), want), wb
+        cnt = c * g
+        packed = torch.zeros((2, cnt, 16), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        half = n // 2
+        assert ctx.msm_partial(bases, d_sc.data_ptr(), half, packed[0].data_ptr(), cnt, window_bits=w) == (c, g)
+        # second "rank": page-locked host scalars, read over PCIe
+        assert ctx.msm_partial(bases, h_sc.data_ptr() + 32 * half, half, packed[1].data_ptr(), cnt, off=half, window_bits=w) == (c, g)
+        two = ctx.msm_finish_gathered(srs.cid, packed.data_ptr(), 2, c, g)
+        assert np.array_equal(zk.jacobian_to_affine(srs.cid, two), want), wb
+        with pytest.raises(zk.ZkError):
+            ctx.msm_partial(bases, d_sc.data_ptr(), n, d_all.data_ptr(), 1)      # buffer too small for the slice sums
+        bases.free()
