@@ -364,6 +364,12 @@ int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value) {
         for (auto& w : ctx->ws_side) w.finish_mode = (int)value;
         return ZK_OK;
     }
+    if (!strcmp(name, "msm_run_len")) {
+        if (value < 0 || value > 64) { zk_set_error("set_option: msm_run_len %ld outside [0, 64]", value); return ZK_ERR_INVALID; }
+        ctx->ws.run_len = (uint32_t)value;
+        for (auto& w : ctx->ws_side) w.run_len = (uint32_t)value;
+        return ZK_OK;
+    }
     if (!strcmp(name, "msm_lanes")) {
         if (value < 1 || value > 1 + zk_ctx::SIDE_LANES) { zk_set_error("set_option: msm_lanes %ld outside [1, %d]", value, 1 + zk_ctx::SIDE_LANES); return ZK_ERR_INVALID; }
         ctx->lanes = (int)value;

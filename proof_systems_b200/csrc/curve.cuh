@@ -48,35 +48,35 @@ template <class F> ZK_HD xyzz_t xyzz_neg(const xyzz_t& p) {
 }
 
 // 2*q for an affine q != identity (mdbl-2008-s-1, a = 0)
-template <class F> ZK_HD xyzz_t xyzz_mdbl(const affine_t& q) {
+template <class F, bool COMPACT = false> ZK_HD xyzz_t xyzz_mdbl(const affine_t& q) {
     xyzz_t r;
     fe U = fe_dbl<F>(q.y);
-    fe V = fe_sqr<F>(U);
-    fe W = fe_mul<F>(U, V);
-    fe S = fe_mul<F>(q.x, V);
-    fe xx = fe_sqr<F>(q.x);
+    fe V = fe_mulx<F, COMPACT>(U, U);
+    fe W = fe_mulx<F, COMPACT>(U, V);
+    fe S = fe_mulx<F, COMPACT>(q.x, V);
+    fe xx = fe_mulx<F, COMPACT>(q.x, q.x);
     fe M = fe_add<F>(fe_dbl<F>(xx), xx);
-    fe X3 = fe_sub<F>(fe_sqr<F>(M), fe_dbl<F>(S));
-    fe Y3 = fe_sub<F>(fe_mul<F>(M, fe_sub<F>(S, X3)), fe_mul<F>(W, q.y));
+    fe X3 = fe_sub<F>(fe_mulx<F, COMPACT>(M, M), fe_dbl<F>(S));
+    fe Y3 = fe_sub<F>(fe_mulx<F, COMPACT>(M, fe_sub<F>(S, X3)), fe_mulx<F, COMPACT>(W, q.y));
     r.X = X3; r.Y = Y3; r.ZZ = V; r.ZZZ = W;
     return r;
 }
 
 // 2*p (dbl-2008-s-1, a = 0).  y = 0 cannot occur on a prime-order curve, but the formula then yields ZZ = 0 anyway.
-template <class F> ZK_HD xyzz_t xyzz_dbl(const xyzz_t& p) {
+template <class F, bool COMPACT = false> ZK_HD xyzz_t xyzz_dbl(const xyzz_t& p) {
     if (xyzz_is_inf(p)) return p;
     xyzz_t r;
     fe U = fe_dbl<F>(p.Y);
-    fe V = fe_sqr<F>(U);
-    fe W = fe_mul<F>(U, V);
-    fe S = fe_mul<F>(p.X, V);
-    fe xx = fe_sqr<F>(p.X);
+    fe V = fe_mulx<F, COMPACT>(U, U);
+    fe W = fe_mulx<F, COMPACT>(U, V);
+    fe S = fe_mulx<F, COMPACT>(p.X, V);
+    fe xx = fe_mulx<F, COMPACT>(p.X, p.X);
     fe M = fe_add<F>(fe_dbl<F>(xx), xx);
-    fe X3 = fe_sub<F>(fe_sqr<F>(M), fe_dbl<F>(S));
-    fe Y3 = fe_sub<F>(fe_mul<F>(M, fe_sub<F>(S, X3)), fe_mul<F>(W, p.Y));
+    fe X3 = fe_sub<F>(fe_mulx<F, COMPACT>(M, M), fe_dbl<F>(S));
+    fe Y3 = fe_sub<F>(fe_mulx<F, COMPACT>(M, fe_sub<F>(S, X3)), fe_mulx<F, COMPACT>(W, p.Y));
     r.X = X3; r.Y = Y3;
-    r.ZZ = fe_mul<F>(V, p.ZZ);
-    r.ZZZ = fe_mul<F>(W, p.ZZZ);
+    r.ZZ = fe_mulx<F, COMPACT>(V, p.ZZ);
+    r.ZZZ = fe_mulx<F, COMPACT>(W, p.ZZZ);
     return r;
 }
 
@@ -105,28 +105,28 @@ template <class F> ZK_HD xyzz_t xyzz_madd(const xyzz_t& p, const affine_t& q) {
 }
 
 // p + q, both XYZZ (add-2008-s), all special cases handled.
-template <class F> ZK_HD xyzz_t xyzz_add(const xyzz_t& p, const xyzz_t& q) {
+template <class F, bool COMPACT = false> ZK_HD xyzz_t xyzz_add(const xyzz_t& p, const xyzz_t& q) {
     if (xyzz_is_inf(q)) return p;
     if (xyzz_is_inf(p)) return q;
-    fe U1 = fe_mul<F>(p.X, q.ZZ);
-    fe U2 = fe_mul<F>(q.X, p.ZZ);
-    fe S1 = fe_mul<F>(p.Y, q.ZZZ);
-    fe S2 = fe_mul<F>(q.Y, p.ZZZ);
+    fe U1 = fe_mulx<F, COMPACT>(p.X, q.ZZ);
+    fe U2 = fe_mulx<F, COMPACT>(q.X, p.ZZ);
+    fe S1 = fe_mulx<F, COMPACT>(p.Y, q.ZZZ);
+    fe S2 = fe_mulx<F, COMPACT>(q.Y, p.ZZZ);
     fe Pd = fe_sub<F>(U2, U1);
     fe Rd = fe_sub<F>(S2, S1);
     if (fe_is_zero(Pd)) {
-        if (fe_is_zero(Rd)) return xyzz_dbl<F>(p);
+        if (fe_is_zero(Rd)) return xyzz_dbl<F, COMPACT>(p);
         return xyzz_identity();
     }
     xyzz_t r;
-    fe PP = fe_sqr<F>(Pd);
-    fe PPP = fe_mul<F>(Pd, PP);
-    fe Q = fe_mul<F>(U1, PP);
-    fe X3 = fe_sub<F>(fe_sub<F>(fe_sqr<F>(Rd), PPP), fe_dbl<F>(Q));
-    fe Y3 = fe_sub<F>(fe_mul<F>(Rd, fe_sub<F>(Q, X3)), fe_mul<F>(S1, PPP));
+    fe PP = fe_mulx<F, COMPACT>(Pd, Pd);
+    fe PPP = fe_mulx<F, COMPACT>(Pd, PP);
+    fe Q = fe_mulx<F, COMPACT>(U1, PP);
+    fe X3 = fe_sub<F>(fe_sub<F>(fe_mulx<F, COMPACT>(Rd, Rd), PPP), fe_dbl<F>(Q));
+    fe Y3 = fe_sub<F>(fe_mulx<F, COMPACT>(Rd, fe_sub<F>(Q, X3)), fe_mulx<F, COMPACT>(S1, PPP));
     r.X = X3; r.Y = Y3;
-    r.ZZ = fe_mul<F>(fe_mul<F>(p.ZZ, q.ZZ), PP);
-    r.ZZZ = fe_mul<F>(fe_mul<F>(p.ZZZ, q.ZZZ), PPP);
+    r.ZZ = fe_mulx<F, COMPACT>(fe_mulx<F, COMPACT>(p.ZZ, q.ZZ), PP);
+    r.ZZZ = fe_mulx<F, COMPACT>(fe_mulx<F, COMPACT>(p.ZZZ, q.ZZZ), PPP);
     return r;
 }
 

@@ -285,6 +285,22 @@ template <class F> ZK_HD fe fe_mul(const fe& a, const fe& b) {
 
 template <class F> ZK_HD fe fe_sqr(const fe& a) { return fe_mul<F>(a, a); }
 
+// Out-of-line product for the LATENCY-bound kernels (the reduction tails of the MSM run a handful of point additions per
+// thread): a point addition with 14 inlined products is ~56 KB of straight-line code that every launch streams through a cold
+// instruction cache; with the product behind a call it is ~3 KB plus one 4 KB body.  The throughput kernels keep the inlined form.
+#if defined(__CUDACC__)
+template <class F> __device__ __noinline__ fe fe_mul_call(fe a, fe b) { return fe_mul<F>(a, b); }
+#else
+template <class F> inline fe fe_mul_call(fe a, fe b) { return fe_mul<F>(a, b); }
+#endif
+// product selected by the code-size policy of the caller
+template <class F, bool COMPACT> ZK_HD fe fe_mulx(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__)
+    if (COMPACT) return fe_mul_call<F>(a, b);
+#endif
+    return fe_mul<F>(a, b);
+}
+
 // canonical integer (8 x u32) -> Montgomery and back (ark: from_bigint / into_bigint)
 template <class F> ZK_HD fe fe_to_mont(const fe& a) { return fe_mul<F>(a, fe_r2<F>()); }
 template <class F> ZK_HD fe fe_from_mont(const fe& a) {

@@ -219,11 +219,63 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
     store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
 }
 
-// Thread-per-bucket variant of the finish pass, for MANY buckets with few partials each: with more buckets than resident
-// quads the pass is throughput bound and the serial formula (one thread per addition) is the cheaper way to spend lanes.
+// Balanced first level of the per-bucket sums.  The task partials lie in bucket order; thread u sums the RUN of `run`
+// consecutive partials [u*run, (u+1)*run) segment by segment (a segment = the part of one bucket inside the run) and writes each
+// segment sum back at the segment's first index.  Every thread executes at most run-1 additions whatever the bucket sizes, so a
+// warp never waits for its longest bucket.  k_bucket_finish_serial then adds, per bucket, the partial at the bucket's first index
+// and those at the multiples of `run` inside it.  (Slots of single-task buckets hold no partial — k_accumulate wrote the bucket
+// itself — and are segments of their own: read and written back, never mixed.)
+template <class F>
+__global__ void __launch_bounds__(128) k_run_sum(const uint32_t* __restrict__ task_off, uint32_t nb, const uint32_t* __restrict__ meta, uint32_t run,
+                                                 uint32_t smax, xyzz_t* partials) {
+    const uint32_t nt = meta[1];
+    const uint64_t i0w = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * run;
+    if (i0w >= nt) return;
+    const uint32_t i0 = (uint32_t)i0w, i1 = min(nt, i0 + run);
+    // largest b with task_off[b] <= i0 (skips the empty buckets that share a start)
+    uint32_t lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(task_off + mid) <= i0) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo, nxt = __ldg(task_off + b + 1), seg = i0;
+    // giant buckets were summed by k_giant_finish: their slots are skipped (a thread wholly inside one does nothing)
+    const bool giants_done = meta[2] <= MSM_MAX_GIANTS;
+    bool skip = giants_done && nxt - __ldg(task_off + b) > smax;
+    if (skip && nxt >= i1) return;
+    xyzz_t acc = load_xyzz(partials + i0);
+    bool dirty = false;
+    for (uint32_t i = i0 + 1; i < i1; i++) {
+        if (skip && i != nxt) continue;
+        const xyzz_t v = load_xyzz(partials + i);
+        if (i == nxt) {
+            if (dirty) store_xyzz(partials + seg, acc);
+            // the bucket that starts at i: usually the next one; behind a stretch of empty buckets, found by bisection
+            b++; nxt = __ldg(task_off + b + 1);
+            if (nxt <= i) {
+                uint32_t l2 = b, h2 = nb;
+                while (h2 - l2 > 1) {
+                    const uint32_t mid = (l2 + h2) >> 1;
+                    if (__ldg(task_off + mid) <= i) l2 = mid; else h2 = mid;
+                }
+                b = l2; nxt = __ldg(task_off + b + 1);
+            }
+            skip = giants_done && nxt - i > smax;
+            seg = i; acc = v; dirty = false;
+        } else {
+            acc = xyzz_add<F, true>(acc, v);
+            dirty = true;
+        }
+    }
+    if (dirty) store_xyzz(partials + seg, acc);
+}
+
+// Thread-per-bucket finish pass, for MANY buckets with few partials each: with more buckets than resident quads the pass is
+// throughput-bound and the quad-cooperative variant below only adds work.  run == 0: the bucket's partials are summed one by
+// one; run > 0: k_run_sum ran first and the bucket's value is spread over its first slot and the multiples of `run` inside it.
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_finish_serial(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
-                                                              uint32_t K, uint32_t smax, const uint32_t* __restrict__ meta, xyzz_t* buckets,
+                                                              uint32_t K, uint32_t smax, const uint32_t* __restrict__ meta, uint32_t run, xyzz_t* buckets,
                                                               const xyzz_t* __restrict__ partials) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
@@ -231,9 +283,13 @@ __global__ void __launch_bounds__(128) k_bucket_finish_serial(const uint32_t* __
     uint32_t sb = (nbk + K - 1) / K;
     if (sb > smax && meta[2] <= MSM_MAX_GIANTS) return;  // k_giant_finish
     if (sb < 2) return;                                  // 0: empty, 1: written by k_accumulate
-    const xyzz_t* p = partials + __ldg(task_off + b);
-    xyzz_t acc = load_xyzz(p);
-    for (uint32_t j = 1; j < sb; j++) acc = xyzz_add<F>(acc, load_xyzz(p + j));
+    const uint32_t a = __ldg(task_off + b);
+    xyzz_t acc = load_xyzz(partials + a);
+    if (run == 0) {
+        for (uint32_t j = 1; j < sb; j++) acc = xyzz_add<F, true>(acc, load_xyzz(partials + a + j));
+    } else {
+        for (uint32_t k = (a / run + 1) * run; k < a + sb; k += run) acc = xyzz_add<F, true>(acc, load_xyzz(partials + k));
+    }
     store_xyzz(buckets + b, acc);
 }
 
@@ -550,13 +606,21 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
                                                                    ws.d_buckets, ws.d_partials);
     STAGE_MARK(4);
     // 5. per-bucket sums of the task partials (+ giants)
-    if (serial_finish)
-        k_bucket_finish_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, ws.d_buckets, ws.d_partials);
-    else
-        k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
-                                                                                  ws.d_buckets, ws.d_partials);
+    // giants first: k_giant_finish reads the untouched partial lists, k_run_sum then rewrites partials in place
     k_giant_finish<F><<<dim3(MSM_MAX_GIANTS, GIANT_SLICES), TREE_THREADS, TREE_QUADS * sizeof(xyzz_t), st>>>(
         ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials, ws.d_giant_slices, ws.d_giant_tickets);
+    if (serial_finish) {
+        const uint32_t run = ws.run_len;
+        if (run) {
+            const size_t threads = (NTmax + run - 1) / run;
+            k_run_sum<F><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ws.d_task_off, (uint32_t)NB, ws.d_meta, run, smax, ws.d_partials);
+            nl += 1;
+        }
+        k_bucket_finish_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, run, ws.d_buckets, ws.d_partials);
+    } else {
+        k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
+                                                                                  ws.d_buckets, ws.d_partials);
+    }
     STAGE_MARK(5);
     // 6. bit-sliced bucket sums
     xyzz_t* d_partial = ws.d_bitsums;

@@ -60,6 +60,7 @@ struct MsmWorkspace {
     uint32_t* d_giant_tickets = nullptr;  // [MSM_MAX_GIANTS] arrival counters (self-resetting)
     int reduce_mode = 1;              // bucket reduction: 0 = bit-sliced sums over all buckets, 1 = two-level row/column sums
     int finish_mode = 0;              // per-bucket sums of task partials: 0 = by shape, 1 = a thread per bucket, 2 = quads per bucket
+    uint32_t run_len = 4;             // k_run_sum: consecutive partials summed per thread before the per-bucket pass (0: off)
     uint32_t chunk = 0;               // K override (0: chosen per call so that the tasks fill whole waves)
     int sm_count = 148;               // SMs of the device (set by the context)
     bool profile = false;             // record an event after every stage

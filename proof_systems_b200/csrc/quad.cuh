@@ -30,11 +30,13 @@ __device__ __forceinline__ fe sel_fe(bool c, const fe& a, const fe& b) {
     return r;
 }
 
-template <class F> __device__ __forceinline__ xyzz_t xyzz_add_quad(const xyzz_t& p, const xyzz_t& q) {
+// COMPACT: the four stage products and the serial fall-back go through the out-of-line product (field.cuh).  Measured neutral
+// to slightly worse for the quad kernels (unlike the serial per-bucket pass, msm.cu), so the default is the inlined form.
+template <class F, bool COMPACT = false> __device__ __forceinline__ xyzz_t xyzz_add_quad(const xyzz_t& p, const xyzz_t& q) {
     const unsigned lane = threadIdx.x & 31, r = lane & 3, base = lane & ~3u;
     const bool r0 = r == 0, r1 = r == 1, r2 = r == 2, odd = (r & 1) != 0, lo = r < 2;
     // stage 1
-    fe m1 = fe_mul<F>(sel_fe(r0, p.X, sel_fe(r1, q.X, sel_fe(r2, p.Y, q.Y))),
+    fe m1 = fe_mulx<F, COMPACT>(sel_fe(r0, p.X, sel_fe(r1, q.X, sel_fe(r2, p.Y, q.Y))),
                       sel_fe(r0, q.ZZ, sel_fe(r1, p.ZZ, sel_fe(r2, q.ZZZ, p.ZZZ))));  // U1 | U2 | S1 | S2
     fe o1 = shfl_xor_fe(m1, 1);
     fe d = odd ? fe_sub<F>(m1, o1) : fe_sub<F>(o1, m1);   // lanes 0,1: P = U2-U1      lanes 2,3: R = S2-S1
@@ -42,15 +44,15 @@ template <class F> __device__ __forceinline__ xyzz_t xyzz_add_quad(const xyzz_t&
     fe Pd = sel_fe(lo, d, d2), Rd = sel_fe(lo, d2, d);
     fe first = sel_fe(odd, o1, m1);                       // lanes 0,1: U1            lanes 2,3: S1
     // stage 2
-    fe m2 = fe_mul<F>(sel_fe(r0, Pd, sel_fe(r1, Rd, sel_fe(r2, p.ZZ, p.ZZZ))),
+    fe m2 = fe_mulx<F, COMPACT>(sel_fe(r0, Pd, sel_fe(r1, Rd, sel_fe(r2, p.ZZ, p.ZZZ))),
                       sel_fe(r0, Pd, sel_fe(r1, Rd, sel_fe(r2, q.ZZ, q.ZZZ))));      // PP | RR | ZZ12 | ZZZ12
     fe PP = shfl_fe(m2, base);
     // stage 3
-    fe m3 = fe_mul<F>(sel_fe(r0, Pd, sel_fe(r1, first, m2)), sel_fe(r == 3, Pd, PP));  // PPP | Q | ZZ3 | W
+    fe m3 = fe_mulx<F, COMPACT>(sel_fe(r0, Pd, sel_fe(r1, first, m2)), sel_fe(r == 3, Pd, PP));  // PPP | Q | ZZ3 | W
     fe PPP = shfl_fe(m3, base);
     fe X3 = fe_sub<F>(fe_sub<F>(m2, PPP), fe_dbl<F>(m3));  // meaningful in lane 1 (RR - PPP - 2Q)
     // stage 4
-    fe m4 = fe_mul<F>(sel_fe(lo, Rd, sel_fe(r2, first, m3)), sel_fe(lo, fe_sub<F>(m3, X3), sel_fe(r2, PPP, PP)));  // - | Ya | Yb | ZZZ3
+    fe m4 = fe_mulx<F, COMPACT>(sel_fe(lo, Rd, sel_fe(r2, first, m3)), sel_fe(lo, fe_sub<F>(m3, X3), sel_fe(r2, PPP, PP)));  // - | Ya | Yb | ZZZ3
     fe Yb = shfl_fe(m4, base + 2);
     fe Y3 = fe_sub<F>(m4, Yb);                             // meaningful in lane 1
     xyzz_t res;
@@ -62,7 +64,7 @@ template <class F> __device__ __forceinline__ xyzz_t xyzz_add_quad(const xyzz_t&
     const bool pinf = xyzz_is_inf(p), qinf = xyzz_is_inf(q);
     if (qinf) return p;
     if (pinf) return q;
-    if (fe_is_zero(Pd)) return xyzz_add<F>(p, q);  // same x: doubling or identity
+    if (fe_is_zero(Pd)) return xyzz_add<F, COMPACT>(p, q);  // same x: doubling or identity
     return res;
 }
 

@@ -11,6 +11,7 @@ ctx = zk.Context(0)
 if os.environ.get("MSM_REDUCE"): ctx.set_option("msm_reduce", int(os.environ["MSM_REDUCE"]))
 if os.environ.get("MSM_CHUNK"): ctx.set_option("msm_chunk", int(os.environ["MSM_CHUNK"]))
 if os.environ.get("MSM_FINISH"): ctx.set_option("msm_finish", int(os.environ["MSM_FINISH"]))
+if os.environ.get("MSM_RUN"): ctx.set_option("msm_run_len", int(os.environ["MSM_RUN"]))
 KS = [int(x) for x in os.environ.get("MSM_LOGS", "8,10,11,12,13,14,15,16").split(",")]
 stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
