@@ -8,6 +8,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ac
 echo "accumulate capture exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ntt_pass -s 8 -c 2 -f -o gpurun_out/prof_ntt $CMD > gpurun_out/ncu_ntt_run.log 2>&1
 echo "ntt capture exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gridsum -s 8 -c 1 -f -o gpurun_out/prof_gridsum $CMD > gpurun_out/ncu_grid_run.log 2>&1
+# (gpurun copies back at most 64 MiB: the third capture keeps the summary sections only)
+timeout 900 ncu --section SpeedOfLight --section LaunchStats --section Occupancy --section WarpStateStats --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --clock-control none -k regex:"k_gridsum|k_run_sum|k_bucket_finish" -s 16 -c 4 -f -o gpurun_out/prof_tails $CMD > gpurun_out/ncu_grid_run.log 2>&1
 echo "gridsum capture exit $?"
 ls -la gpurun_out | head -30
