@@ -195,3 +195,14 @@ def test_commit_evaluations_batch_and_lanes(ctx, orc, pallas_srs):
     finally:
         ctx.set_option("msm_lanes", 4)
     srs.close()
+
+
+def test_one_generator_srs_regression_bytes_on_device(ctx, orc):
+    """precomputed_srs.rs:139-155: the serialised one-generator SRS decodes to the curve generator (pallas.rs:10-15,
+    vesta.rs:10-15) and re-encodes to the same bytes, on both curves."""
+    from test_srs_file import GENERATOR_Y, SRS_ONE_GENERATOR_HEX
+    raw = np.frombuffer(bytes.fromhex(SRS_ONE_GENERATOR_HEX)[4:37], dtype=np.uint8).reshape(1, 33)
+    for name, cid, fid in (("pallas", zk.PALLAS, orc.FP), ("vesta", zk.VESTA, orc.FQ)):
+        pt = ctx.decompress_points(cid, raw)
+        assert orc.limbs_to_ints(orc.from_mont(fid, pt.reshape(2, 4))) == [1, GENERATOR_Y[name]]
+        assert np.array_equal(ctx.compress_points(cid, pt), raw)

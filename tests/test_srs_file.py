@@ -73,3 +73,26 @@ def test_multi_chunk_bases_and_malformed_input(tmp_path, pallas_srs):
         open(p, "wb").write(bad)
         with pytest.raises(ValueError):
             srs_file.read_srs(p)
+
+
+# poly-commitment/src/precomputed_srs.rs:139-155: rmp-serde of SRS::new(vec![G::generator()], G::generator()), both curves
+SRS_ONE_GENERATOR_HEX = ("9291c421010000000000000000000000000000000000000000000000000000000000000000"
+                         "c421010000000000000000000000000000000000000000000000000000000000000000")
+# curves/src/pasta/curves/pallas.rs:10-15, vesta.rs:10-15
+GENERATOR_Y = {"pallas": 12418654782883325593414442427049395787963493412651469444558597405572177144507,
+               "vesta": 11426906929455361843568202299992114520848200991084027513389447476559454104162}
+
+
+def test_one_generator_srs_regression_bytes(orc, tmp_path):
+    raw = bytes.fromhex(SRS_ONE_GENERATOR_HEX)
+    p = str(tmp_path / "one.srs")
+    open(p, "wb").write(raw)
+    f = srs_file.read_srs(p)
+    assert f.compressed and f.g.shape == (1, 33) and np.array_equal(f.g[0], f.h) and not f.lagrange_bases
+    srs_file.write_srs(p, f)
+    assert open(p, "rb").read() == raw
+    # the oracle's decompression of those 33 bytes is the curve generator of the reference (y = the smaller root: flag 0)
+    for name, cid, fid in (("pallas", orc.PALLAS, orc.FP), ("vesta", orc.VESTA, orc.FQ)):
+        pt = orc.decompress(cid, f.g.tobytes())[0]
+        xy = orc.from_mont(fid, pt.reshape(2, 4))
+        assert orc.limbs_to_ints(xy) == [1, GENERATOR_Y[name]]
