@@ -521,12 +521,13 @@ int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, con
     ZK_CUDA(cudaSetDevice(ctx->device));
     const fe* d_sc = nullptr;
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, scalars) == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+    const bool known = cudaPointerGetAttributes(&attr, scalars) == cudaSuccess;
+    if (!known) cudaGetLastError();   // some drivers report "invalid value" for pageable pointers
+    if (known && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
         d_sc = (const fe*)scalars;
-    } else if (attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+    } else if (known && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
         d_sc = (const fe*)attr.devicePointer;          // page-locked: read over PCIe by the recode kernel
     } else {
-        cudaGetLastError();
         int rc = ctx_ensure((void**)&ctx->d_scalars, &ctx->cap_scalars, n * sizeof(fe));
         if (rc) return rc;
         ZK_CUDA(cudaMemcpyAsync(ctx->d_scalars, scalars, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));

@@ -1,5 +1,6 @@
 // ntt.cu — kernels and launch plan of the Pasta-field NTT (see ntt.cuh for semantics and reference call sites).
 #include "ntt.cuh"
+#include "ntt_butterfly.cuh"
 
 namespace zkb {
 
@@ -105,23 +106,24 @@ template <class F> __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(
     }
     __syncthreads();
 
-    // decimation in frequency: natural order in, bit-reversed order out (undone by the store's index map)
+    // decimation in frequency: natural order in, bit-reversed order out (undone by the store's index map).  The butterfly and
+    // its index map live in ntt_butterfly.cuh (also compiled for the host and checked against the oracle there).  A radix-2^2
+    // schedule (two layers per shared-memory round trip, same header) was measured: identical times — the pass is bound by
+    // the integer pipes, not by shared memory or barriers — so the simpler radix-2 loop stays.
     for (int l = (int)p.log_s - 1; l >= 0; l--) {
-        const unsigned h = 1u << l;
         for (unsigned bidx = tid; bidx < (S * T) / 2; bidx += NTT_THREADS) {
-            unsigned c = bidx >> (p.log_s - 1), j = bidx & (S / 2 - 1);
-            unsigned grp = j >> l, pos = j & (h - 1);
-            unsigned i0 = (grp << (l + 1)) + pos, i1 = i0 + h;
+            const unsigned c = bidx >> (p.log_s - 1), j = bidx & (S / 2 - 1);
+            unsigned i0, tw;
+            ntt_index2(j, (unsigned)l, i0, tw);
             uint32_t* a0 = sm + c * PITCH + i0;
-            uint32_t* a1 = sm + c * PITCH + i1;
+            uint32_t* a1 = a0 + (1u << l);
             fe u, v;
 #pragma unroll
             for (int k = 0; k < 8; k++) { u.v[k] = a0[k * T * PITCH]; v.v[k] = a1[k * T * PITCH]; }
-            fe s = fe_add<F>(u, v);
-            fe d = fe_sub<F>(u, v);
-            if (l != 0) d = fe_mul<F>(d, load_fe_nc(p.small + ((size_t)pos << (9 - l))));  // w_S^(pos*S/2h) = w_1024^(pos*512/h)
+            if (l != 0) { const fe w = load_fe_nc(p.small + tw); ntt_bfly2<F>(u, v, &w); }   // w_S^(pos*S/2h) = w_1024^(pos*512/h)
+            else ntt_bfly2<F>(u, v, nullptr);
 #pragma unroll
-            for (int k = 0; k < 8; k++) { a0[k * T * PITCH] = s.v[k]; a1[k * T * PITCH] = d.v[k]; }
+            for (int k = 0; k < 8; k++) { a0[k * T * PITCH] = u.v[k]; a1[k * T * PITCH] = v.v[k]; }
         }
         __syncthreads();
     }

@@ -3,6 +3,7 @@
 // the GPU will execute can be checked against the CPU oracle on a machine without a GPU.  Test infrastructure only.
 #include <cstring>
 #include "../../proof_systems_b200/csrc/curve.cuh"
+#include "../../proof_systems_b200/csrc/ntt_butterfly.cuh"
 using namespace zkb;
 
 template <class F> static void mul_(const uint32_t* a, const uint32_t* b, uint32_t* r) {
@@ -64,4 +65,44 @@ extern "C" void hm_sum_affine(int cid, const uint32_t* pts, size_t n, uint32_t* 
     }
     affine_t A = cid == 0 ? xyzz_to_affine<FpParams>(acc) : xyzz_to_affine<FqParams>(acc);
     memcpy(out_aff, &A, sizeof A);
+}
+
+
+// The layer schedule of k_ntt_pass on one column of S = 2^log_s rows (in place, natural order in, bit-reversed order out):
+// radix 4: an odd log_s starts with one radix-2 layer, then radix-2^2 units; radix 2: plain layers.  small = w_1024^i, 512 entries.
+template <class F> static void ntt_column_(uint32_t* data, unsigned log_s, const uint32_t* small32, int radix) {
+    const unsigned S = 1u << log_s;
+    fe* x = reinterpret_cast<fe*>(data);
+    const fe* small = reinterpret_cast<const fe*>(small32);
+    int l = (int)log_s - 1;
+    if (radix == 4 && (log_s & 1) && l >= 0) {
+        for (unsigned j = 0; j < S / 2; j++) {
+            unsigned i0, tw;
+            ntt_index2(j, (unsigned)l, i0, tw);
+            ntt_bfly2<F>(x[i0], x[i0 + (1u << l)], l ? &small[tw] : nullptr);
+        }
+        l--;
+    }
+    while (l >= 0) {
+        if (radix == 4) {
+            for (unsigned j = 0; j < S / 4; j++) {
+                unsigned e0, q, tA, tB, tC;
+                ntt_index4(j, (unsigned)l, e0, q, tA, tB, tC);
+                const unsigned h = 1u << l;
+                ntt_bfly4<F>(x[e0], x[e0 + q], x[e0 + h], x[e0 + h + q], small[tA], small[tB], l >= 2 ? &small[tC] : nullptr);
+            }
+            l -= 2;
+        } else {
+            for (unsigned j = 0; j < S / 2; j++) {
+                unsigned i0, tw;
+                ntt_index2(j, (unsigned)l, i0, tw);
+                ntt_bfly2<F>(x[i0], x[i0 + (1u << l)], l ? &small[tw] : nullptr);
+            }
+            l--;
+        }
+    }
+}
+extern "C" void hm_ntt_column(int fid, uint32_t* data, unsigned log_s, const uint32_t* small, int radix) {
+    if (fid == 0) ntt_column_<FpParams>(data, log_s, small, radix);
+    else ntt_column_<FqParams>(data, log_s, small, radix);
 }

@@ -19,7 +19,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "proof_systems_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def hm():
-    deps = [SRC, os.path.join(CSRC, "field.cuh"), os.path.join(CSRC, "curve.cuh")]
+    deps = [SRC, os.path.join(CSRC, "field.cuh"), os.path.join(CSRC, "curve.cuh"), os.path.join(CSRC, "ntt_butterfly.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC])
     return ctypes.CDLL(SO)
@@ -130,3 +130,22 @@ def test_xyzz_group_law_vs_oracle(hm, orc, request, name):
     hm.hm_sum_affine(cid, p32(pts.view(np.uint32)), ctypes.c_size_t(n), p32(out.view(np.uint32)))
     ones = np.zeros((n, 4), dtype=np.uint64); ones[:, 0] = 1
     assert np.array_equal(out, orc.msm(cid, pts, ones))
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+@pytest.mark.parametrize("radix", [2, 4])
+def test_ntt_tile_layer_schedule_vs_oracle(hm, orc, fid, radix):
+    """The butterflies and index maps k_ntt_pass executes (csrc/ntt_butterfly.cuh: radix-2 layers and radix-2^2 units) on one
+    column, every log_s the tile pass uses: the bit-reversed result must be the oracle's forward NTT of that size."""
+    f = orc.FP if fid == 0 else orc.FQ
+    m = orc.MODULUS[f]
+    w1024 = orc.fe_int(f, orc.root_of_unity(f, 10))
+    small = orc.to_mont(f, orc.ints_to_limbs([pow(w1024, i, m) for i in range(512)]))
+    for log_s in range(0, 11):
+        S = 1 << log_s
+        a = orc.to_mont(f, orc.random_scalars(f, S, seed=100 + log_s))
+        buf = np.ascontiguousarray(a).copy()
+        hm.hm_ntt_column(fid, p32(buf.view(np.uint32)), log_s, p32(small.view(np.uint32)), radix)
+        rev = [int(format(k, f"0{log_s}b")[::-1], 2) if log_s else 0 for k in range(S)]
+        got = buf[rev]                      # out[k] sits in row bitrev(k)
+        assert np.array_equal(got, orc.ntt(f, a)), (log_s, radix)
