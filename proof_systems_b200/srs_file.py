@@ -92,6 +92,8 @@ class _Reader:
             raise ValueError(f"msgpack: expected bin8 records at byte {self.p}")
         ln = int(self.a[self.p + k + 1])
         stride = k + 2 + ln
+        if count > (self.a.shape[0] - self.p) // stride:
+            raise ValueError("msgpack: truncated point array")
         block = self.a[self.p:self.p + count * stride]
         if block.shape[0] != count * stride:
             raise ValueError("msgpack: truncated point array")
@@ -106,6 +108,13 @@ class _Reader:
 def read_srs(path: str) -> SrsFile:
     with open(path, "rb") as f:
         buf = f.read()
+    try:
+        return _parse(path, buf)
+    except (IndexError, struct.error, OverflowError, MemoryError) as e:   # ran off the end / absurd length fields
+        raise ValueError(f"{path}: truncated or malformed msgpack ({type(e).__name__})") from e
+
+
+def _parse(path: str, buf: bytes) -> SrsFile:
     r = _Reader(buf)
     fields = r.array_len()
     if fields not in (2, 3):

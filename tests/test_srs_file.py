@@ -96,3 +96,28 @@ def test_one_generator_srs_regression_bytes(orc, tmp_path):
         pt = orc.decompress(cid, f.g.tobytes())[0]
         xy = orc.from_mont(fid, pt.reshape(2, 4))
         assert orc.limbs_to_ints(xy) == [1, GENERATOR_Y[name]]
+
+
+def test_reader_rejects_corrupted_files_cleanly(tmp_path, vesta_srs):
+    """Any truncation or byte flip of a valid file either still parses or raises ValueError — never another exception."""
+    import random
+    flag = np.zeros((8, 1), dtype=np.uint8)
+    g65 = np.concatenate([vesta_srs.g_xy_canon[:8], flag], axis=1)
+    bases = {4: np.concatenate([vesta_srs.lag_small_canon[3:7], flag[:4]], axis=1).reshape(4, 1, 65)}
+    good = str(tmp_path / "good.srs")
+    srs_file.write_srs(good, srs_file.SrsFile(g=g65, h=g65[0], lagrange_bases=bases))
+    raw = open(good, "rb").read()
+    rng = random.Random(9)
+    bad = str(tmp_path / "bad.srs")
+    for trial in range(300):
+        b = bytearray(raw)
+        if trial % 3 == 0:
+            b = b[: rng.randrange(len(b))]
+        else:
+            for _ in range(rng.randrange(1, 4)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        open(bad, "wb").write(bytes(b))
+        try:
+            srs_file.read_srs(bad)
+        except ValueError:
+            pass
