@@ -51,3 +51,21 @@ def test_product_does_not_reference_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", os.path.join(pkg, "libzkb200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/zkb200.h is a C ABI: it must compile as C11 (-pedantic) and link against the library; without a GPU the first
+    call fails loudly with ZK_ERR_NO_DEVICE."""
+    import subprocess
+    src = tmp_path / "abi_c.c"
+    src.write_text('#include "zkb200.h"\n#include <stdio.h>\n'
+                   'int main(void) { zk_ctx* ctx = NULL; int rc = zk_ctx_create(0, &ctx);\n'
+                   '  printf("%d|%s\\n", rc, zk_last_error()); if (rc == ZK_OK) zk_ctx_destroy(ctx); return 0; }\n')
+    exe = tmp_path / "abi_c"
+    lib_dir = os.path.join(ROOT, "proof_systems_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L", lib_dir, "-lzkb200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    rc = int(out.split("|")[0])
+    import torch
+    assert rc == (0 if torch.cuda.is_available() else -3), out
