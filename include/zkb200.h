@@ -64,7 +64,10 @@ int zk_ctx_set_profile(zk_ctx* ctx, int enabled);
 /* Tuning knobs.  "msm_chunk": sorted entries per accumulation task (0 = built-in default).
  *                "msm_lanes": 1..4 concurrent MSM pipelines used by calls that carry several independent MSMs
  *                (zk_msm_batch, zk_srs_commit_non_hiding with several chunks, zk_srs_commit_evaluations_batch, the L/R pair of
- *                zk_ipa_round_lr); default 4.  One MSM's latency-bound reduction tail overlaps another's accumulation. */
+ *                zk_ipa_round_lr); default 4.  One MSM's latency-bound reduction tail overlaps another's accumulation.
+ *                A/B switches used by tools/ and DESIGN.md's measurements: "msm_reduce" (0 bit-sliced, 1 two-level bucket
+ *                reduction; default 1), "msm_finish" (0 by shape, 1 thread per bucket, 2 quads per bucket), "msm_run_len"
+ *                (partials per thread in the balanced first level of the per-bucket sums, 0 = off; default 4). */
 int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value);
 int zk_ctx_last_stage_ms(const zk_ctx* ctx, float* out, size_t capacity);
 

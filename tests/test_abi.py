@@ -69,3 +69,21 @@ def test_header_is_plain_c_and_links(tmp_path):
     rc = int(out.split("|")[0])
     import torch
     assert rc == (0 if torch.cuda.is_available() else -3), out
+
+
+def test_cpp_host_layer_compiles_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/zkb200.hpp (the C++ mirror of SRS<G> / Radix2EvaluationDomain / the open rounds) and its test driver compile
+    warning-free; without a GPU the Context constructor throws zkb200::Error{ZK_ERR_NO_DEVICE}."""
+    import subprocess
+    import torch
+    lib_dir = os.path.join(ROOT, "proof_systems_b200")
+    exe = str(tmp_path / "host_layer")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_layer.cpp"), "-L", lib_dir, "-lzkb200", f"-Wl,-rpath,{lib_dir}", "-o", exe])
+    if torch.cuda.is_available():
+        return
+    blob = tmp_path / "in.bin"
+    np = __import__("numpy")
+    np.zeros(1 + 8 * 4 + 8 + 6 * 4 + 4 * 4 + 2 * 4 + 8, dtype="<u8").tofile(str(blob))
+    run = subprocess.run([exe, str(blob), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert run.returncode != 0 and not os.path.exists(str(tmp_path / "out.bin"))
