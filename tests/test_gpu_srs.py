@@ -206,3 +206,25 @@ def test_one_generator_srs_regression_bytes_on_device(ctx, orc):
         pt = ctx.decompress_points(cid, raw)
         assert orc.limbs_to_ints(orc.from_mont(fid, pt.reshape(2, 4))) == [1, GENERATOR_Y[name]]
         assert np.array_equal(ctx.compress_points(cid, pt), raw)
+
+
+def test_polycomm_serialization_regression_bytes_on_device(ctx, orc, vesta_srs):
+    """ser_regression_canonical_polycomm (poly-commitment/tests/commitment.rs:345-385): srs.commit(DensePolynomial::rand(300, rng),
+    6, rng) on SRS::<Vesta>::create(128) with StdRng seed [0; 32] — commit_non_hiding, mask_custom and the point compression all
+    on the device path — serialises to the reference's hard-coded bytes."""
+    import json
+    import os
+
+    from test_ser_regression import GOLDEN, msgpack_points, padded, polycomm_inputs
+    G = vesta_srs
+    coeffs, blinders = polycomm_inputs(orc)
+    srs = zk.SRS(ctx, G.cid, G.g[:128], G.mont_points(G.h_xy_canon)[0])
+    com = srs.commit_custom(coeffs, 6, blinders)                         # == srs.commit(&poly, 6, rng) with those blinders
+    assert len(com) == 6
+    pts33 = ctx.compress_points(G.cid, com.chunks)
+    raw = msgpack_points([bytes(p) for p in pts33], struct_prefix=b"\x91")
+    want = json.load(open(GOLDEN))["polycomm_vesta_srs128_deg300_chunks6"]
+    assert padded(raw, len(want)) == want
+    with pytest.raises(BlindersDontMatch):
+        srs.commit_custom(coeffs, 6, blinders[:5])
+    srs.close()
