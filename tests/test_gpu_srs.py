@@ -228,3 +228,16 @@ def test_polycomm_serialization_regression_bytes_on_device(ctx, orc, vesta_srs):
     with pytest.raises(BlindersDontMatch):
         srs.commit_custom(coeffs, 6, blinders[:5])
     srs.close()
+
+
+def test_opening_proof_serialization_regression_bytes_on_device(ctx, orc, vesta_srs):
+    """ser_regression_canonical_opening_proof (poly-commitment/tests/commitment.rs:388-443): SRS::open with the seven folding
+    rounds — the L/R MSMs, the inner products, the folds of a and b, the final sg — run by the device (zk.IpaRounds, csrc/ipa.cu)
+    and the host-side transcript replayed around them (tests/open_replay.py) serialises to the reference's hard-coded bytes."""
+    import json
+
+    from open_replay import DeviceRounds, first_opening_proof_bytes
+    from test_ser_regression import GOLDEN, padded
+    raw = first_opening_proof_bytes(orc, vesta_srs, lambda g, a, b: DeviceRounds(orc, zk, ctx, g, a, b))
+    want = json.load(open(GOLDEN))["opening_proof_vesta_srs128"]
+    assert padded(raw, len(want)) == want

@@ -79,3 +79,21 @@ def test_polycomm_bytes_with_the_oracle(orc, expected, vesta_srs):
     raw = msgpack_points(masked, struct_prefix=b"\x91")
     key = "polycomm_vesta_srs128_deg300_chunks6"
     assert padded(raw, len(expected[key])) == expected[key]
+
+
+def test_poseidon_restatement_matches_the_reference_vectors():
+    """poseidon/tests/test_vectors/kimchi.json (Fp, PlonkSpongeConstantsKimchi): pins tests/kimchi_transcript.py's permutation"""
+    from kimchi_transcript import PARAMS, ArithmeticSponge
+    for v in PARAMS["fp_hash_vectors"]:
+        sp = ArithmeticSponge("fp")
+        sp.absorb([int.from_bytes(bytes.fromhex(x), "little") for x in v["input"]])
+        assert sp.squeeze().to_bytes(32, "little").hex() == v["output"]
+
+
+def test_opening_proof_bytes_with_the_oracle(orc, expected, vesta_srs):
+    """ser_regression_canonical_opening_proof (commitment.rs:388-443): the whole of SRS::open — combine_polys, the sponge, the
+    group map, 7 folding rounds, delta, z1, z2, sg — replayed with the oracle doing the group arithmetic."""
+    from open_replay import OracleRounds, first_opening_proof_bytes
+    raw = first_opening_proof_bytes(orc, vesta_srs, lambda g, a, b: OracleRounds(orc, g, a, b))
+    key = "opening_proof_vesta_srs128"
+    assert padded(raw, len(expected[key])) == expected[key]
