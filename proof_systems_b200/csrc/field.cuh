@@ -40,6 +40,13 @@ ZK_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("subc.cc.u32 
 ZK_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 ZK_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 ZK_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// plain 64-bit product unpacked into halves: ptxas keeps it a stand-alone IMAD.WIDE.U32 (a mul.lo/mul.hi pair followed by
+// carry adds is re-fused into the carry-chained IMAD.WIDE.U32.X)
+ZK_D void mul_wide_split(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+    uint64_t t;
+    ZK_ASM("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
+    ZK_ASM("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
+}
 ZK_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; ZK_ASM("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 ZK_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; ZK_ASM("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 ZK_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; ZK_ASM("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -56,6 +63,7 @@ inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b -
 inline uint32_t subc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a - b - zk_cf()); }
 inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
 inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline void mul_wide_split(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) { uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
 inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)mul_lo(a, b) + c; zk_cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
 inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)mul_lo(a, b) + c + zk_cf(); zk_cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
 inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)mul_hi(a, b) + c + zk_cf(); zk_cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
@@ -223,6 +231,16 @@ template <class F> ZK_HD void mont_reduce_row(uint32_t (&P)[9], uint32_t (&S)[9]
     P[8] = addc(P[8], 0u);
 }
 
+// ZK_MUL_PLAIN_PER_ROW — pipe-balancing experiment prepared for the next GPU round (DESIGN.md "next levers"); 0 = the shipped,
+// measured form (the macro below then expands to exactly the original instruction sequence).  K = 1..6: the K highest products
+// a_j * b_i of every row (j = 7, 6, 5, ...) become PLAIN wide multiplies — 2.1 cycles on the FMA pipe instead of 4.0 for the
+// carry-chained form, and off the carry chains — added in with two carry adds each on the half-idle ALU pipe.  Bit-exact in every
+// setting (tests/test_device_math_host.py builds them all).  SASS of one product (IMAD.WIDE.U32.X / IMAD.WIDE.U32 / IADD3.X):
+//   K = 0: 69 / 21 / 63     K = 2: 55 / 35 / 91     K = 5: 34 / 56 / 133 (both pipes at about 300 cycles by the measured rates)
+#ifndef ZK_MUL_PLAIN_PER_ROW
+#define ZK_MUL_PLAIN_PER_ROW 0
+#endif
+
 // Montgomery product a*b/R mod m, fully reduced.  Inputs < m.
 template <class F> ZK_HD fe fe_mul(const fe& a, const fe& b) {
     uint32_t P[9], S[9];
@@ -246,25 +264,30 @@ template <class F> ZK_HD fe fe_mul(const fe& a, const fe& b) {
         // shift right one limb: t' = S + P1 + (P[2..8] << 32); then t' += a * b_i
         const uint32_t bi = b.v[i];
         uint32_t nP[9], nS[9];
+#if ZK_MUL_PLAIN_PER_ROW > 0
+        // products a_j * b_i, j >= 8 - ZK_MUL_PLAIN_PER_ROW, as stand-alone wide multiplies (off the carry chains)
+        uint32_t tl[8], th[8];
+#pragma unroll
+        for (int j = 8 - ZK_MUL_PLAIN_PER_ROW; j < 8; j++) mul_wide_split(a.v[j], bi, tl[j], th[j]);
+#define ZK_ROW_PAIR(dst, k, j, add_lo, add_hi)                                                   \
+        if (j >= 8 - ZK_MUL_PLAIN_PER_ROW) { dst[k] = addc_cc(tl[j], add_lo); dst[k + 1] = addc_cc(th[j], add_hi); } \
+        else { dst[k] = madc_lo_cc(a.v[j], bi, add_lo); dst[k + 1] = madc_hi_cc(a.v[j], bi, add_hi); }
+#else
+#define ZK_ROW_PAIR(dst, k, j, add_lo, add_hi) { dst[k] = madc_lo_cc(a.v[j], bi, add_lo); dst[k + 1] = madc_hi_cc(a.v[j], bi, add_hi); }
+#endif
         nP[0] = add_cc(S[0], P[1]);                  // carry is worth nS[0]
-        nS[0] = madc_lo_cc(a.v[1], bi, P[2]);
-        nS[1] = madc_hi_cc(a.v[1], bi, P[3]);
-        nS[2] = madc_lo_cc(a.v[3], bi, P[4]);
-        nS[3] = madc_hi_cc(a.v[3], bi, P[5]);
-        nS[4] = madc_lo_cc(a.v[5], bi, P[6]);
-        nS[5] = madc_hi_cc(a.v[5], bi, P[7]);
-        nS[6] = madc_lo_cc(a.v[7], bi, P[8]);
-        nS[7] = madc_hi_cc(a.v[7], bi, 0u);
+        ZK_ROW_PAIR(nS, 0, 1, P[2], P[3])
+        ZK_ROW_PAIR(nS, 2, 3, P[4], P[5])
+        ZK_ROW_PAIR(nS, 4, 5, P[6], P[7])
+        ZK_ROW_PAIR(nS, 6, 7, P[8], 0u)
         nS[8] = addc(0u, 0u);
         nP[0] = mad_lo_cc(a.v[0], bi, nP[0]);
         nP[1] = madc_hi_cc(a.v[0], bi, S[1]);
-        nP[2] = madc_lo_cc(a.v[2], bi, S[2]);
-        nP[3] = madc_hi_cc(a.v[2], bi, S[3]);
-        nP[4] = madc_lo_cc(a.v[4], bi, S[4]);
-        nP[5] = madc_hi_cc(a.v[4], bi, S[5]);
-        nP[6] = madc_lo_cc(a.v[6], bi, S[6]);
-        nP[7] = madc_hi_cc(a.v[6], bi, S[7]);
+        ZK_ROW_PAIR(nP, 2, 2, S[2], S[3])
+        ZK_ROW_PAIR(nP, 4, 4, S[4], S[5])
+        ZK_ROW_PAIR(nP, 6, 6, S[6], S[7])
         nP[8] = addc(S[8], 0u);
+#undef ZK_ROW_PAIR
         mont_reduce_row<F>(nP, nS);
 #pragma unroll
         for (int k = 0; k < 9; k++) { P[k] = nP[k]; S[k] = nS[k]; }

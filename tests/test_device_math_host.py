@@ -149,3 +149,23 @@ def test_ntt_tile_layer_schedule_vs_oracle(hm, orc, fid, radix):
         rev = [int(format(k, f"0{log_s}b")[::-1], 2) if log_s else 0 for k in range(S)]
         got = buf[rev]                      # out[k] sits in row bitrev(k)
         assert np.array_equal(got, orc.ntt(f, a)), (log_s, radix)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+def test_split_product_variants_are_bit_exact(orc, k):
+    """field.cuh's ZK_MUL_PLAIN_PER_ROW = k (k products per row as stand-alone wide multiplies + carry adds: the pipe-balancing
+    experiment of DESIGN.md) computes the same Montgomery product as the shipped form, on edge values and random ones."""
+    so = os.path.join(HERE, "host_math", f"libhost_math_k{k}.so")
+    deps = [SRC, os.path.join(CSRC, "field.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", f"-DZK_MUL_PLAIN_PER_ROW={k}", "-o", so, SRC])
+    lib = ctypes.CDLL(so)
+    for fid in (0, 1):
+        f = orc.FP if fid == 0 else orc.FQ
+        m = orc.MODULUS[f]
+        vals = sample_values(orc, f, 400, seed=70 + k)
+        a = orc.ints_to_limbs(vals)
+        b = orc.ints_to_limbs(vals[::-1])
+        got = run_bin(lib, "hm_mul", fid, a, b)
+        rinv = pow(1 << 256, -1, m)
+        assert orc.limbs_to_ints(got) == [x * y * rinv % m for x, y in zip(vals, vals[::-1])]
