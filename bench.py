@@ -48,41 +48,76 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + clock-event reasons DURING the timed region.  NVML is polled from a thread every 2 ms (the timed region of a
+    default run is tens of milliseconds: `nvidia-smi -lms` needs about a second before its first line, which is why round 1's
+    sampler came back empty); nvidia-smi is the fallback when NVML cannot be loaded."""
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.stop_flag, self.thread, self.h, self.nv = index, [], False, None, None, None
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                ids = [x for x in visible.split(",") if x.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        masks = (nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap)
+        while not self.stop_flag:
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, tuple(bool(r & m) for m in masks)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) >= 6:
-                self.samples.append(parts)
+        self.samples, self.stop_flag = [], False
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        if self.h is None:
+            return self._smi_once()
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[1][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
+                "source": "NVML, 2 ms period over the timed region"}
+
+    def _smi_once(self):
+        """fallback: one nvidia-smi query right after the timed region"""
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        for query in (q, "clocks.sm,clocks.max.sm"):
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={query}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout.strip().splitlines()
+                parts = [x.strip() for x in out[0].split(",")]
+                if parts[0].isdigit():
+                    reasons = [n for i, n in enumerate(self.NAMES) if len(parts) > 2 + i and parts[2 + i].lower().startswith("active")]
+                    return {"sm_mhz": int(parts[0]), "sm_max_mhz": int(parts[1]), "reasons": reasons, "samples": 1,
+                            "source": "nvidia-smi, one query after the timed region (NVML unavailable)"}
+            except Exception:
+                continue
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 def splitmix64_limbs(seed, n):
@@ -388,6 +423,10 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        # a timed result that differs from the CPU oracle is not a measurement
+        print("bench.py: the timed MSM result differs from the CPU oracle", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

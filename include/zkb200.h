@@ -61,13 +61,11 @@ uint64_t zk_ctx_launch_count(const zk_ctx* ctx);
  * zk_ctx_last_stage_ms fills out[0..5] = MSM stages {recode, plan, scatter, accumulate, finish, bitsum} of the last
  * MSM and out[6] = all kernels of the last NTT call, in milliseconds.  capacity >= 8. */
 int zk_ctx_set_profile(zk_ctx* ctx, int enabled);
-/* Tuning knobs.  "msm_chunk": sorted entries per accumulation task (0 = built-in default).
- *                "msm_lanes": 1..4 concurrent MSM pipelines used by calls that carry several independent MSMs
- *                (zk_msm_batch, zk_srs_commit_non_hiding with several chunks, zk_srs_commit_evaluations_batch, the L/R pair of
- *                zk_ipa_round_lr); default 4.  One MSM's latency-bound reduction tail overlaps another's accumulation.
- *                A/B switches used by tools/ and DESIGN.md's measurements: "msm_reduce" (0 bit-sliced, 1 two-level bucket
- *                reduction; default 1), "msm_finish" (0 by shape, 1 thread per bucket, 2 quads per bucket), "msm_run_len"
- *                (partials per thread in the balanced first level of the per-bucket sums, 0 = off; default 4). */
+/* Tuning knobs.  "msm_chunk": sorted entries per accumulation task (0 = built-in default: the tasks fill the machine once).
+ *                "msm_batch": 1..16 MSMs of one call fused into ONE pipeline with one bucket group per MSM (zk_msm_batch,
+ *                zk_srs_commit_non_hiding with several chunks, zk_srs_commit_evaluations_batch, the L/R pair of
+ *                zk_ipa_round_lr): every latency-bound stage is paid once per batch; default 16.
+ *                "msm_wave_threads": accumulation threads per SM the task count is sized for (0 = built-in default). */
 int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value);
 int zk_ctx_last_stage_ms(const zk_ctx* ctx, float* out, size_t capacity);
 
@@ -164,7 +162,7 @@ int zk_srs_commit_evaluations_non_hiding(zk_srs* srs, size_t domain_size, const 
                                          size_t evals_domain_size, uint64_t out_xy[8]);
 /* k commit_evaluations_non_hiding calls on one domain in a single call (the reference issues the 15 witness columns
  * concurrently from rayon workers, kimchi/src/prover.rs:329-351): evals_mont = k x domain_size, out_xy = k x 8.  The
- * independent MSMs run on concurrent lanes (zk_ctx_set_option "msm_lanes", default 4). */
+ * independent MSMs run as one fused pipeline (zk_ctx_set_option "msm_batch"). */
 int zk_srs_commit_evaluations_batch(zk_srs* srs, size_t domain_size, const uint64_t* evals_mont, size_t k, uint64_t* out_xy);
 int zk_srs_mask_custom(zk_srs* srs, const uint64_t* chunks_xy, size_t n_chunks, const uint64_t* blinders_mont,
                        size_t n_blinders, uint64_t* out_xy);

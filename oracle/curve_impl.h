@@ -262,9 +262,12 @@ static void CN(msm_pippenger)(CN(jac) *r, const CN(aff) *bases, const uint64_t *
  */
 static int CN(decompress)(CN(aff) *r, const uint8_t in[33]) {
     uint8_t flags = in[32];
-    if (flags & 0x40) { CN(aff_set_inf)(r); return 1; }
     uint64_t xc[4];
     memcpy(xc, in, 32);
+    /* ark-serialize: SWFlags::from_u8 knows only 0x00 / 0x80 / 0x40; the field element must be canonical (x < modulus) */
+    if ((flags & 0x3f) != 0 || (flags & 0xc0) == 0xc0) return 0;
+    if (BF(geq_mod)(xc)) return 0;
+    if (flags & 0x40) { CN(aff_set_inf)(r); return 1; }
     BF(t) x, rhs, y, five, ny;
     uint64_t c5[4] = {5, 0, 0, 0};
     BF(to_mont)(&x, xc);

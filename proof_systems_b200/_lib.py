@@ -12,7 +12,9 @@ BASE_FIELD = {PALLAS: FP, VESTA: FQ}
 SCALAR_FIELD = {PALLAS: FQ, VESTA: FP}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libzkb200.so")
+# ZKB200_LIB: an alternative BUILD of the same CUDA library (tools/mul_variants.sh times the field-product variants
+# libzkb200_k<K>.so against the shipped one); never a different implementation — there is no CPU fallback to select.
+_SO = os.environ.get("ZKB200_LIB") or os.path.join(_HERE, "libzkb200.so")
 
 
 def library_path() -> str:

@@ -50,103 +50,45 @@ static void xyzz_to_jac_out(int curve, const host::hxyzz& p, uint64_t out[12]) {
     memcpy(out, &j, sizeof j);
 }
 
-int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* d_scalars, int mont, int window_bits,
-                   uint64_t out_xyz[12]) {
-    if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
-    MsmResultShape shape;
-    unsigned nl = 0;
-    int rc;
-    if (bases->b.curve == ZK_PALLAS)
-        rc = msm_run<FpParams, FqParams>(bases->b, off, n, d_scalars, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
-    else
-        rc = msm_run<FqParams, FpParams>(bases->b, off, n, d_scalars, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
-    if (rc) return rc;
-    ctx->launches += nl;
-    host::hxyzz r = host::identity();
-    if (shape.groups) {
-        r = bases->b.curve == ZK_PALLAS ? msm_finish_t<host::HFp>(ctx->ws.h_bitsums, shape.c, shape.groups)
-                                        : msm_finish_t<host::HFq>(ctx->ws.h_bitsums, shape.c, shape.groups);
-    }
-    xyzz_to_jac_out(bases->b.curve, r, out_xyz);
-    return ZK_OK;
-}
-
-static int ctx_lanes_init(zk_ctx* ctx) {
-    if (ctx->ev_fork) return ZK_OK;
-    for (int l = 0; l < zk_ctx::SIDE_LANES; l++) {
-        ZK_CUDA(cudaStreamCreateWithFlags(&ctx->side[l], cudaStreamNonBlocking));
-        ctx->ws_side[l].sm_count = ctx->ws.sm_count;
-        ctx->ws_side[l].defer_sync = true;
-    }
-    for (int l = 0; l < 1 + zk_ctx::SIDE_LANES; l++)
-        for (int s = 0; s < 2; s++) ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[l][s], cudaEventDisableTiming));
-    ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    return ZK_OK;
-}
-
-int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, const size_t* offs, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
+int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
                  uint64_t* out_xyz) {
     if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
-    if (k == 0) return ZK_OK;
-    // one lane when profiling (stage events are per workspace) or when the caller pinned the task length
-    const int lanes = (k == 1 || ctx->profile || ctx->lanes <= 1) ? 1 : (int)std::min<size_t>(k, (size_t)std::min(ctx->lanes, 1 + zk_ctx::SIDE_LANES));
-    if (lanes == 1) {
-        for (size_t j = 0; j < k; j++) {
-            int rc = ctx_msm_device(ctx, bases, offs[j], n, d_scalars[j], mont, window_bits, out_xyz + 12 * j);
-            if (rc) return rc;
-        }
-        return ZK_OK;
-    }
-    int rc = ctx_lanes_init(ctx);
-    if (rc) return rc;
     const bool pallas = bases->b.curve == ZK_PALLAS;
-    ZK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));            // the scalars are ready on the main stream
-    for (int l = 1; l < lanes; l++) ZK_CUDA(cudaStreamWaitEvent(ctx->side[l - 1], ctx->ev_fork, 0));
-    std::vector<MsmResultShape> shapes(k);
-    auto lane_ws = [&](int l) -> MsmWorkspace& { return l == 0 ? ctx->ws : ctx->ws_side[l - 1]; };
-    auto collect = [&](size_t j) -> int {
-        const int l = (int)(j % lanes), slot = (int)((j / lanes) & 1);
-        ZK_CUDA(cudaEventSynchronize(ctx->ev_lane[l][slot]));
-        host::hxyzz r = host::identity();
-        const MsmResultShape& sh = shapes[j];
-        if (sh.groups) {
-            const xyzz_t* h = lane_ws(l).h_bitsums + (size_t)slot * sh.groups * sh.c;
-            r = pallas ? msm_finish_t<host::HFp>(h, sh.c, sh.groups) : msm_finish_t<host::HFq>(h, sh.c, sh.groups);
-        }
-        xyzz_to_jac_out(bases->b.curve, r, out_xyz + 12 * j);
-        return ZK_OK;
-    };
-    const bool keep_defer = ctx->ws.defer_sync;
-    ctx->ws.defer_sync = true;
-    size_t collected = 0;
-    rc = ZK_OK;
-    for (size_t j = 0; j < k && rc == ZK_OK; j++) {
-        const int l = (int)(j % lanes), slot = (int)((j / lanes) & 1);
-        // the slot's previous user is MSM j - 2*lanes: finish it on the host before its pinned copy is overwritten
-        while (rc == ZK_OK && j >= 2 * (size_t)lanes && collected <= j - 2 * (size_t)lanes) rc = collect(collected++);
-        if (rc) break;
-        MsmWorkspace& ws = lane_ws(l);
-        cudaStream_t st = l == 0 ? ctx->stream : ctx->side[l - 1];
-        ws.h_slot = (unsigned)slot;
-        ws.chunk = ctx->ws.chunk;
+    // MSMs per pipeline: the context's limit, and no more than keeps the sorted entry list below 2^28 entries (1 GiB of scratch)
+    const unsigned c_eff = bases->b.c ? bases->b.c : (window_bits ? (unsigned)window_bits : (unsigned)msm_default_window(n, false));
+    const size_t per_msm = std::max<size_t>(1, n * msm_num_windows(std::max(2u, c_eff)));
+    size_t fuse = std::min<size_t>((size_t)std::max(1, ctx->batch), std::max<size_t>(1, ((size_t)1 << 28) / per_msm));
+    if (ctx->profile) fuse = 1;   // stage times are those of ONE MSM (zk_ctx_last_stage_ms)
+    for (size_t j0 = 0; j0 < k; j0 += fuse) {
+        const unsigned cnt = (unsigned)std::min(fuse, k - j0);
+        MsmResultShape shape;
         unsigned nl = 0;
-        rc = pallas ? msm_run<FpParams, FqParams>(bases->b, offs[j], n, d_scalars[j], mont != 0, (unsigned)window_bits, ws, st, &shapes[j], &nl)
-                    : msm_run<FqParams, FpParams>(bases->b, offs[j], n, d_scalars[j], mont != 0, (unsigned)window_bits, ws, st, &shapes[j], &nl);
-        ctx->launches += nl;
-        if (rc == ZK_OK && cudaEventRecord(ctx->ev_lane[l][slot], st) != cudaSuccess) { zk_set_error("msm: cudaEventRecord failed"); rc = ZK_ERR_CUDA; }
-    }
-    ctx->ws.defer_sync = keep_defer;
-    ctx->ws.h_slot = 0;
-    if (rc != ZK_OK) {   // drain whatever was enqueued before reporting
-        cudaStreamSynchronize(ctx->stream);
-        for (int l = 1; l < lanes; l++) cudaStreamSynchronize(ctx->side[l - 1]);
-        return rc;
-    }
-    while (collected < k) {
-        rc = collect(collected++);
+        ctx->ws.h_slot = 0;
+        int rc = pallas ? msm_run<FpParams, FqParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl)
+                        : msm_run<FqParams, FpParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
         if (rc) return rc;
+        ctx->launches += nl;
+        for (unsigned j = 0; j < cnt; j++) {
+            host::hxyzz r = host::identity();
+            if (shape.groups) {
+                const xyzz_t* h = ctx->ws.h_bitsums + (size_t)j * shape.groups * shape.c;
+                r = pallas ? msm_finish_t<host::HFp>(h, shape.c, shape.groups) : msm_finish_t<host::HFq>(h, shape.c, shape.groups);
+            }
+            xyzz_to_jac_out(bases->b.curve, r, out_xyz + 12 * (j0 + j));
+        }
     }
-    // every lane has been waited for through its events: later work on the main stream is ordered after all of it
+    return ZK_OK;
+}
+
+int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* d_scalars, int mont, int window_bits,
+                   uint64_t out_xyz[12]) {
+    return ctx_msm_many(ctx, bases, off, n, &d_scalars, 1, mont, window_bits, out_xyz);
+}
+
+static int ctx_side_streams_init(zk_ctx* ctx) {
+    if (ctx->ev_fork) return ZK_OK;
+    for (int l = 0; l < zk_ctx::SIDE_STREAMS; l++) ZK_CUDA(cudaStreamCreateWithFlags(&ctx->side[l], cudaStreamNonBlocking));
+    ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     return ZK_OK;
 }
 
@@ -308,12 +250,9 @@ void zk_ctx_destroy(zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     msm_workspace_free(ctx->ws);
-    for (int l = 0; l < zk_ctx::SIDE_LANES; l++) {
+    for (int l = 0; l < zk_ctx::SIDE_STREAMS; l++)
         if (ctx->side[l]) { cudaStreamSynchronize(ctx->side[l]); cudaStreamDestroy(ctx->side[l]); }
-        msm_workspace_free(ctx->ws_side[l]);
-    }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    for (auto& le : ctx->ev_lane) for (auto& e : le) if (e) cudaEventDestroy(e);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
     if (ctx->d_gather_sum) cudaFree(ctx->d_gather_sum);
@@ -352,27 +291,14 @@ int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value) {
         ctx->ws.chunk = (uint32_t)value;
         return ZK_OK;
     }
-    if (!strcmp(name, "msm_reduce")) {
-        if (value < 0 || value > 1) { zk_set_error("set_option: msm_reduce %ld outside [0, 1]", value); return ZK_ERR_INVALID; }
-        ctx->ws.reduce_mode = (int)value;
-        for (auto& w : ctx->ws_side) w.reduce_mode = (int)value;
+    if (!strcmp(name, "msm_batch")) {
+        if (value < 1 || value > (long)MSM_MAX_BATCH) { zk_set_error("set_option: msm_batch %ld outside [1, %u]", value, MSM_MAX_BATCH); return ZK_ERR_INVALID; }
+        ctx->batch = (int)value;
         return ZK_OK;
     }
-    if (!strcmp(name, "msm_finish")) {
-        if (value < 0 || value > 2) { zk_set_error("set_option: msm_finish %ld outside [0, 2]", value); return ZK_ERR_INVALID; }
-        ctx->ws.finish_mode = (int)value;
-        for (auto& w : ctx->ws_side) w.finish_mode = (int)value;
-        return ZK_OK;
-    }
-    if (!strcmp(name, "msm_run_len")) {
-        if (value < 0 || value > 64) { zk_set_error("set_option: msm_run_len %ld outside [0, 64]", value); return ZK_ERR_INVALID; }
-        ctx->ws.run_len = (uint32_t)value;
-        for (auto& w : ctx->ws_side) w.run_len = (uint32_t)value;
-        return ZK_OK;
-    }
-    if (!strcmp(name, "msm_lanes")) {
-        if (value < 1 || value > 1 + zk_ctx::SIDE_LANES) { zk_set_error("set_option: msm_lanes %ld outside [1, %d]", value, 1 + zk_ctx::SIDE_LANES); return ZK_ERR_INVALID; }
-        ctx->lanes = (int)value;
+    if (!strcmp(name, "msm_wave_threads")) {
+        if (value < 0 || value > 2048) { zk_set_error("set_option: msm_wave_threads %ld outside [0, 2048]", value); return ZK_ERR_INVALID; }
+        ctx->ws.wave_threads = (uint32_t)value;
         return ZK_OK;
     }
     zk_set_error("set_option: unknown option '%s'", name);
@@ -458,7 +384,7 @@ static int points_codec(zk_ctx* ctx, int curve_id, int mode, const void* in, siz
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_bad);
     if (e != cudaSuccess) { zk_set_error("%s: %s", what, cudaGetErrorString(e)); return ZK_ERR_CUDA; }
     if (rc == ZK_OK && bad) {
-        zk_set_error(mode == 0 ? "%s: %u of %zu x-coordinates are not on the curve" : "%s: %u of %zu points have a non-canonical coordinate", what, bad, n);
+        zk_set_error(mode == 0 ? "%s: %u of %zu encodings are invalid (x off the curve, x >= modulus, or unknown flag bits)" : "%s: %u of %zu points have a non-canonical coordinate", what, bad, n);
         return ZK_ERR_INVALID;
     }
     return rc;
@@ -503,10 +429,9 @@ int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const
         if (n) ZK_CUDA(cudaMemcpyAsync(ctx->d_scalars, scalars, k * n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
         d_sc = ctx->d_scalars;
     }
-    std::vector<size_t> offs(k, off);
     std::vector<const fe*> scs(k);
     for (size_t j = 0; j < k; j++) scs[j] = d_sc + j * n;
-    return ctx_msm_many(ctx, bases, offs.data(), n, scs.data(), k, scalars_are_mont, window_bits, out_xyz);
+    return ctx_msm_many(ctx, bases, off, n, scs.data(), k, scalars_are_mont, window_bits, out_xyz);
 }
 
 // Multi-GPU sharding: this rank's MSM is left on the device as its slice sums and nothing is synchronised, so
@@ -538,8 +463,8 @@ int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, con
     ctx->ws.d_T_out = (xyzz_t*)d_out;
     ctx->ws.d_T_cap = capacity_points;
     int rc = bases->b.curve == ZK_PALLAS
-                 ? msm_run<FpParams, FqParams>(bases->b, off, n, d_sc, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl)
-                 : msm_run<FqParams, FpParams>(bases->b, off, n, d_sc, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
+                 ? msm_run<FpParams, FqParams>(bases->b, off, n, &d_sc, 1, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl)
+                 : msm_run<FqParams, FpParams>(bases->b, off, n, &d_sc, 1, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
     ctx->ws.d_T_out = nullptr;
     ctx->ws.d_T_cap = 0;
     ctx->launches += nl;
@@ -659,7 +584,7 @@ int zk_ntt_batch(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, size
         ZK_CUDA(cudaStreamSynchronize(ctx->stream));
         return ZK_OK;
     }
-    rc = ctx_lanes_init(ctx);
+    rc = ctx_side_streams_init(ctx);
     if (rc) return rc;
     cudaStream_t s_in = ctx->side[0], s_out = ctx->side[1];
     const size_t chunks = (batch + per - 1) / per;

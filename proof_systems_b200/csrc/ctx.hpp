@@ -10,12 +10,11 @@ struct zk_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::mutex mu;                       // a context serialises its calls (SRS: Sync + Send, SURVEY.md §8b "Threading")
-    zkb::MsmWorkspace ws;                // lane 0 (runs on `stream`)
-    static constexpr int SIDE_LANES = 3; // independent MSMs of one call (a batch, the L/R pair of an IPA round) run on up to
-    zkb::MsmWorkspace ws_side[SIDE_LANES];   // 1 + SIDE_LANES lanes: the latency-bound tails of one overlap the
-    cudaStream_t side[SIDE_LANES] = {};      // throughput-bound accumulation of the others
-    int lanes = 1 + SIDE_LANES;          // zk_ctx_set_option("msm_lanes")
-    cudaEvent_t ev_fork = nullptr, ev_lane[1 + SIDE_LANES][2] = {};
+    zkb::MsmWorkspace ws;                // scratch of the MSM pipeline (runs on `stream`)
+    static constexpr int SIDE_STREAMS = 2;   // copy-in / copy-out streams of the pipelined host-pointer NTT (zk_ntt_batch)
+    cudaStream_t side[SIDE_STREAMS] = {};
+    int batch = (int)zkb::MSM_MAX_BATCH; // zk_ctx_set_option("msm_batch"): MSMs of one call fused into one pipeline
+    cudaEvent_t ev_fork = nullptr;
     zkb::fe* d_scalars = nullptr;        // staging for host-pointer MSM calls
     size_t cap_scalars = 0;
     zkb::fe* d_ntt = nullptr;            // staging for host-pointer NTT calls
@@ -44,8 +43,8 @@ namespace zkb {
 int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* d_scalars, int mont, int window_bits,
                    uint64_t out_xyz[12]);
 int ctx_ensure(void** p, size_t* cap, size_t bytes);
-// k independent MSMs over the same bases slice, scalars j at d_scalars + j * stride (device memory, ordered after ctx->stream);
-// lanes = 1 .. 1 + SIDE_LANES concurrent pipelines.  Results (Jacobian) to out_xyz + 12 j.
-int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, const size_t* offs, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
+// k independent MSMs over the same bases slice [off, off + n), scalars j at d_scalars[j] (device memory, ordered after
+// ctx->stream), fused into pipelines of up to ctx->batch MSMs (msm.cuh).  Results (Jacobian) to out_xyz + 12 j.
+int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
                  uint64_t* out_xyz);
 }  // namespace zkb

@@ -84,8 +84,16 @@ template <class F> __global__ void __launch_bounds__(128) k_decompress(const uin
     affine_t r;
     r.x = fe_zero();
     r.y = fe_zero();
+    // ark-serialize's SWFlags::from_u8 accepts exactly three flag values (0x00, 0x80, 0x40): stray low bits and the
+    // infinity + sign combination are rejected, and the field deserialiser checks x < modulus (what the reference's
+    // deserialize_with_mode(Compress::Yes, Validate::Yes) enforces through SerdeAs, utils/src/serialization.rs:65-106).
+    const fe xc = load_le_bytes(p);
+    if ((flags & 0x3f) != 0 || (flags & 0xc0) == 0xc0 || !fe_lt_modulus<F>(xc)) {
+        atomicAdd(bad, 1u);
+        store_affine(out + i, r);
+        return;
+    }
     if (!(flags & 0x40)) {
-        const fe xc = load_le_bytes(p);
         const fe x = fe_to_mont<F>(xc);
         fe five = fe_zero();
         five.v[0] = 5;

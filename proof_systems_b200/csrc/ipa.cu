@@ -100,7 +100,7 @@ template <class FS> static int inner_product(zk_ipa* s, const fe* x, const fe* y
 
 }  // namespace zkb
 
-// L and R of one round: both scalar vectors are expanded on the main stream, the two MSMs run on two lanes
+// L and R of one round: both scalar vectors are expanded on the main stream, the two MSMs run as ONE fused pipeline
 template <class FS> static int ipa_expand_and_msm(zk_ipa* s, size_t h, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12]) {
     zk_ctx* ctx = s->ctx;
     const unsigned blocks = (unsigned)((s->n0 + 255) / 256);
@@ -109,10 +109,9 @@ template <class FS> static int ipa_expand_and_msm(zk_ipa* s, size_t h, uint64_t 
     ZK_CUDA(cudaGetLastError());
     ctx->launches += 2;
     const size_t len = s->n0 < s->bases->b.n ? s->n0 : s->bases->b.n;   // positions past the SRS are identity padding
-    const size_t offs[2] = {0, 0};
     const fe* scs[2] = {s->d_sc, s->d_sc + s->n0};
     uint64_t out[24];
-    int rc = ctx_msm_many(ctx, s->bases, offs, len, scs, 2, /*mont=*/1, 0, out);
+    int rc = ctx_msm_many(ctx, s->bases, 0, len, scs, 2, /*mont=*/1, 0, out);
     if (rc) return rc;
     memcpy(out_l_xyz, out, 96);
     memcpy(out_r_xyz, out + 12, 96);

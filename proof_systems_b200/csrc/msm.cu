@@ -54,14 +54,17 @@ void msm_bases_free(MsmBases& b) {
 }
 
 // ---------------------------------------------------------------------------------------------- recode + histogram
-// One thread per scalar: Montgomery -> canonical if asked (VariableBaseMSM::msm == into_bigint + msm_bigint), then
-// signed base-2^c digits d_w in (-2^(c-1), 2^(c-1)];  digit w of scalar i at digits[w*n + i]; per-bucket counts.
+// One thread per scalar of one MSM of the batch (blockIdx.y): Montgomery -> canonical if asked (VariableBaseMSM::msm ==
+// into_bigint + msm_bigint), then signed base-2^c digits d_w in (-2^(c-1), 2^(c-1)]; digit w of scalar i of MSM j at
+// digits[(j*nwin + w)*n + i]; per-bucket counts.  Bucket group of (MSM j, window w): j*gpm + (per_window ? w : 0).
 template <class FS>
-__global__ void k_recode(const fe* scalars, int scalars_mont, size_t n, unsigned c, unsigned nwin, unsigned groups_per_window,
-                         int32_t* digits, uint32_t* counts) {
+__global__ void k_recode(MsmScalarSet sc, int scalars_mont, size_t n, unsigned c, unsigned nwin, unsigned gpm, int per_window,
+                         int32_t* digits, uint32_t* counts, uint32_t* meta) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { meta[2] = 0; meta[4] = 0; }   // giants, plan tiles done
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fe s = load_fe_nc(scalars + i);
+    const unsigned j = blockIdx.y;
+    fe s = load_fe_nc(sc.p[j] + i);
     if (scalars_mont) s = fe_from_mont<FS>(s);
     const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
     const uint32_t B = half;
@@ -77,21 +80,23 @@ __global__ void k_recode(const fe* scalars, int scalars_mont, size_t n, unsigned
         int32_t sd;
         if (d > half) { sd = (int32_t)d - (int32_t)(1u << c); carry = 1; }
         else { sd = (int32_t)d; carry = 0; }
-        digits[(size_t)w * n + i] = sd;
+        digits[((size_t)j * nwin + w) * n + i] = sd;
         // warp-aggregated histogram update: lanes that hit the same bucket (kimchi's all-ones columns: all of them) elect
         // one lane to add their count — one atomic per distinct bucket per warp instead of one per lane
         const uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
-        const uint32_t key = sd != 0 ? (groups_per_window ? w : 0) * B + (mag - 1) : 0xffffffffu;
+        const uint32_t key = sd != 0 ? (j * gpm + (per_window ? w : 0)) * B + (mag - 1) : 0xffffffffu;
         const uint32_t peers = __match_any_sync(__activemask(), key);
         if (sd != 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
     }
 }
 
-// Single-CTA planning pass over the histogram: exclusive scans of the bucket counts (-> offsets of the sorted entry list)
-// and of the per-bucket task counts s_b = ceil(n_b / K) (-> task_off).  Buckets with more than smax tasks ("giant": the
-// all-ones witness columns of kimchi put ~n entries in one bucket) are listed for k_giant_finish.
-// Clears counts (re-used as scatter cursors).
-// 64-bit lanes carry (entry count << 32 | task count): one block scan yields both prefix sums.
+// Planning pass over the histogram: exclusive scans of the bucket counts (-> offsets of the sorted entry list) and of the
+// per-bucket task counts s_b = ceil(n_b / K) (-> task_off).  One CTA per tile of 4096 buckets; the tiles are chained (tile t
+// spins on tile t-1's published inclusive total — tiles are dispatched in order, so the predecessor is always resident), which
+// keeps the scan a single launch for any batch size.  64-bit lanes carry (entry count << 32 | task count): one scan yields both.
+// Buckets with more than smax tasks ("giant": the all-ones witness columns of kimchi put ~n entries in one bucket,
+// SURVEY.md §3.1) are listed; the last tile to finish lays out their side areas behind the main slots.  Clears counts
+// (re-used as scatter cursors).
 __device__ __forceinline__ uint64_t block_excl_scan_1024(uint64_t v, uint64_t* warp_sums, uint64_t* tile_total) {
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint64_t x = v;
@@ -118,56 +123,84 @@ __device__ __forceinline__ uint64_t block_excl_scan_1024(uint64_t v, uint64_t* w
     return excl;
 }
 
-constexpr unsigned PLAN_PER_THREAD = 4;
+constexpr unsigned PLAN_PER_THREAD = 4, PLAN_TILE = 1024 * PLAN_PER_THREAD;
 __global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offsets, uint32_t* task_off, uint32_t nb, uint32_t K, uint32_t smax,
-                                                 uint32_t* meta /* [0] entries, [1] tasks, [2] giants */, uint32_t* giants) {
+                                                 uint32_t* meta, uint32_t* giants, uint64_t* chain, uint32_t* chain_flag, uint32_t epoch) {
     __shared__ uint64_t warp_sums[32];
-    __shared__ uint64_t tile_total, carry;
-    const unsigned tid = threadIdx.x;
-    if (tid == 0) { carry = 0; meta[2] = 0; }
-    __syncthreads();
-    for (uint32_t base = 0; base < nb; base += 1024 * PLAN_PER_THREAD) {
-        const uint32_t i0 = base + tid * PLAN_PER_THREAD;
-        uint32_t v[PLAN_PER_THREAD];
-        uint64_t pk[PLAN_PER_THREAD], sum = 0;
+    __shared__ uint64_t tile_total, prefix_s;
+    __shared__ uint32_t last_s;
+    const unsigned tid = threadIdx.x, tile = blockIdx.x;
+    const uint32_t i0 = tile * PLAN_TILE + tid * PLAN_PER_THREAD;
+    uint32_t v[PLAN_PER_THREAD];
+    uint64_t pk[PLAN_PER_THREAD], sum = 0;
 #pragma unroll
-        for (unsigned k = 0; k < PLAN_PER_THREAD; k++) {
-            v[k] = i0 + k < nb ? counts[i0 + k] : 0;
-            if (i0 + k < nb) counts[i0 + k] = 0;
-            pk[k] = ((uint64_t)v[k] << 32) | ((v[k] + K - 1) / K);
-            sum += pk[k];
-        }
-        uint64_t ex = carry + block_excl_scan_1024(sum, warp_sums, &tile_total);
-#pragma unroll
-        for (unsigned k = 0; k < PLAN_PER_THREAD; k++) {
-            if (i0 + k < nb) {
-                offsets[i0 + k] = (uint32_t)(ex >> 32);
-                task_off[i0 + k] = (uint32_t)ex;
-                if ((uint32_t)pk[k] > smax) {
-                    uint32_t gi = atomicAdd(&meta[2], 1u);
-                    if (gi < MSM_MAX_GIANTS) giants[gi] = i0 + k;
-                }
-            }
-            ex += pk[k];
-        }
-        __syncthreads();
-        if (tid == 0) carry += tile_total;
-        __syncthreads();
+    for (unsigned k = 0; k < PLAN_PER_THREAD; k++) {
+        v[k] = i0 + k < nb ? counts[i0 + k] : 0;
+        if (i0 + k < nb) counts[i0 + k] = 0;
+        pk[k] = ((uint64_t)v[k] << 32) | ((v[k] + K - 1) / K);
+        sum += pk[k];
     }
-    if (tid == 0) { offsets[nb] = (uint32_t)(carry >> 32); task_off[nb] = (uint32_t)carry; meta[0] = (uint32_t)(carry >> 32); meta[1] = (uint32_t)carry; }
+    uint64_t ex = block_excl_scan_1024(sum, warp_sums, &tile_total);
+    if (tid == 0) {
+        uint64_t prefix = 0;
+        if (tile > 0) {
+            volatile uint32_t* f = chain_flag + (tile - 1);
+            while (*f != epoch) { }
+            __threadfence();
+            prefix = *(volatile uint64_t*)(chain + (tile - 1));
+        }
+        *(volatile uint64_t*)(chain + tile) = prefix + tile_total;
+        __threadfence();
+        *(volatile uint32_t*)(chain_flag + tile) = epoch;
+        prefix_s = prefix;
+    }
+    __syncthreads();
+    ex += prefix_s;
+#pragma unroll
+    for (unsigned k = 0; k < PLAN_PER_THREAD; k++) {
+        if (i0 + k < nb) {
+            offsets[i0 + k] = (uint32_t)(ex >> 32);
+            task_off[i0 + k] = (uint32_t)ex;
+            if ((uint32_t)pk[k] > smax) {
+                uint32_t gi = atomicAdd(&meta[2], 1u);
+                if (gi < MSM_MAX_GIANTS) { giants[gi] = i0 + k; giants[MSM_MAX_GIANTS + gi] = (uint32_t)pk[k]; }
+            }
+        }
+        ex += pk[k];
+    }
+    if (tile == gridDim.x - 1 && tid == 0) {
+        const uint64_t tot = prefix_s + tile_total;
+        offsets[nb] = (uint32_t)(tot >> 32); task_off[nb] = (uint32_t)tot;
+        meta[0] = (uint32_t)(tot >> 32); meta[1] = (uint32_t)tot;
+    }
+    // the last tile to finish sees the complete giant list: main slots first, then one side area per listed giant
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last_s = atomicAdd(&meta[4], 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (last_s && tid == 0) {
+        __threadfence();
+        const uint32_t ng = min(*(volatile uint32_t*)(meta + 2), MSM_MAX_GIANTS);
+        const uint32_t nt = (uint32_t)(*(volatile uint64_t*)(chain + (gridDim.x - 1)));
+        uint32_t excess = 0;
+        for (uint32_t r = 0; r < ng; r++) excess += *(volatile uint32_t*)(giants + MSM_MAX_GIANTS + r) - 1;
+        uint32_t base = nt - excess;
+        meta[3] = base;
+        for (uint32_t r = 0; r < ng; r++) { giants[2 * MSM_MAX_GIANTS + r] = base; base += *(volatile uint32_t*)(giants + MSM_MAX_GIANTS + r); }
+    }
 }
 
 // Counting-sort scatter: entry (point index | sign) of every non-zero digit goes to its bucket's range.
-__global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned nwin, unsigned groups_per_window, size_t base_off,
+__global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned nwin, unsigned batch, unsigned gpm, int per_window, size_t base_off,
                           size_t table_stride, int use_table, const uint32_t* offsets, uint32_t* cursors, uint32_t* entries) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = id < n * nwin;
+    const bool in_range = id < n * nwin * batch;
     int32_t sd = in_range ? digits[id] : 0;
-    unsigned w = (unsigned)(id / n);
-    size_t i = id - (size_t)w * n;
+    const unsigned jw = (unsigned)(id / n), j = jw / nwin, w = jw - j * nwin;
+    size_t i = id - (size_t)jw * n;
     const uint32_t B = 1u << (c - 1);
     uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd);
-    uint32_t key = sd != 0 ? (groups_per_window ? w : 0) * B + (mag - 1) : 0xffffffffu;
+    uint32_t key = sd != 0 ? (j * gpm + (per_window ? w : 0)) * B + (mag - 1) : 0xffffffffu;
     // warp-aggregated cursor bump (see k_recode): the leader reserves a run, every peer takes its rank inside it
     const uint32_t peers = __match_any_sync(0xffffffffu, key);
     const unsigned lane = threadIdx.x & 31, leader = (unsigned)(__ffs(peers) - 1);
@@ -180,16 +213,40 @@ __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned 
     entries[pos] = (uint32_t)pidx | (sd < 0 ? 0x80000000u : 0u);
 }
 
+// ---------------------------------------------------------------------------------------------- slots of the partial list
+// Task t of bucket b leaves its partial in a SLOT.  Main slots follow bucket order: bucket b owns [slot_of(b), slot_of(b+1));
+// that is its task range, except that a listed giant owns ONE main slot (its total, written by k_giant_finish) and keeps its
+// task partials in a side area behind the main slots.  With no giants (uniform scalars) slot == task index.
+struct GiantList {
+    const uint32_t* bucket;   // [ng]
+    const uint32_t* tasks;    // [ng]
+    const uint32_t* area;     // [ng] first slot of the side area
+    uint32_t ng;
+};
+__device__ __forceinline__ GiantList giant_list(const uint32_t* __restrict__ meta, const uint32_t* __restrict__ giants) {
+    GiantList g;
+    g.ng = min(__ldg(meta + 2), MSM_MAX_GIANTS);
+    g.bucket = giants; g.tasks = giants + MSM_MAX_GIANTS; g.area = giants + 2 * MSM_MAX_GIANTS;
+    return g;
+}
+__device__ __forceinline__ uint32_t slot_of(const uint32_t* __restrict__ task_off, uint32_t b, const GiantList& g) {
+    uint32_t s = __ldg(task_off + b);
+    for (uint32_t r = 0; r < g.ng; r++)
+        if (__ldg(g.bucket + r) < b) s -= __ldg(g.tasks + r) - 1;
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------------- accumulation
 // Task t belongs to the bucket b with task_off[b] <= t < task_off[b+1]; the bucket's n_b sorted entries are cut into
 // s_b = ceil(n_b / K) nearly equal parts, so no task crosses a bucket boundary and every thread sums <= K points with
-// XYZZ mixed additions.  Single-task buckets are written directly, the others leave one partial per task.
+// XYZZ mixed additions and leaves one partial in its slot.
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__ points, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
-                                                    uint32_t K, const uint32_t* __restrict__ meta, xyzz_t* buckets, xyzz_t* partials) {
+                                                    uint32_t K, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ giants,
+                                                    xyzz_t* partials) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= meta[1]) return;
+    if (t >= __ldg(meta + 1)) return;
     // upper_bound(task_off[0..nb], t) - 1
     uint32_t lo = 0, hi = nb;  // invariant: task_off[lo] <= t < task_off[hi]
     while (hi - lo > 1) {
@@ -216,239 +273,186 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
         if (sign) q.y = fe_neg<F>(q.y);
         acc = xyzz_madd<F>(acc, q);
     }
-    store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
-}
-
-// Balanced first level of the per-bucket sums.  The task partials lie in bucket order; thread u sums the RUN of `run`
-// consecutive partials [u*run, (u+1)*run) segment by segment (a segment = the part of one bucket inside the run) and writes each
-// segment sum back at the segment's first index.  Every thread executes at most run-1 additions whatever the bucket sizes, so a
-// warp never waits for its longest bucket.  k_bucket_finish_serial then adds, per bucket, the partial at the bucket's first index
-// and those at the multiples of `run` inside it.  (Slots of single-task buckets hold no partial — k_accumulate wrote the bucket
-// itself — and are segments of their own: read and written back, never mixed.)
-template <class F>
-__global__ void __launch_bounds__(128) k_run_sum(const uint32_t* __restrict__ task_off, uint32_t nb, const uint32_t* __restrict__ meta, uint32_t run,
-                                                 uint32_t smax, xyzz_t* partials) {
-    const uint32_t nt = meta[1];
-    const uint64_t i0w = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * run;
-    if (i0w >= nt) return;
-    const uint32_t i0 = (uint32_t)i0w, i1 = min(nt, i0 + run);
-    // largest b with task_off[b] <= i0 (skips the empty buckets that share a start)
-    uint32_t lo = 0, hi = nb;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(task_off + mid) <= i0) lo = mid; else hi = mid;
-    }
-    uint32_t b = lo, nxt = __ldg(task_off + b + 1), seg = i0;
-    // giant buckets were summed by k_giant_finish: their slots are skipped (a thread wholly inside one does nothing)
-    const bool giants_done = meta[2] <= MSM_MAX_GIANTS;
-    bool skip = giants_done && nxt - __ldg(task_off + b) > smax;
-    if (skip && nxt >= i1) return;
-    xyzz_t acc = load_xyzz(partials + i0);
-    bool dirty = false;
-    for (uint32_t i = i0 + 1; i < i1; i++) {
-        if (skip && i != nxt) continue;
-        const xyzz_t v = load_xyzz(partials + i);
-        if (i == nxt) {
-            if (dirty) store_xyzz(partials + seg, acc);
-            // the bucket that starts at i: usually the next one; behind a stretch of empty buckets, found by bisection
-            b++; nxt = __ldg(task_off + b + 1);
-            if (nxt <= i) {
-                uint32_t l2 = b, h2 = nb;
-                while (h2 - l2 > 1) {
-                    const uint32_t mid = (l2 + h2) >> 1;
-                    if (__ldg(task_off + mid) <= i) l2 = mid; else h2 = mid;
-                }
-                b = l2; nxt = __ldg(task_off + b + 1);
-            }
-            skip = giants_done && nxt - i > smax;
-            seg = i; acc = v; dirty = false;
-        } else {
-            acc = xyzz_add<F, true>(acc, v);
-            dirty = true;
+    uint32_t dest = t;
+    const GiantList g = giant_list(meta, giants);
+    if (g.ng) {
+        uint32_t excess = 0, mine = 0xffffffffu;
+        for (uint32_t r = 0; r < g.ng; r++) {
+            const uint32_t gb = __ldg(g.bucket + r);
+            if (gb < b) excess += __ldg(g.tasks + r) - 1;
+            else if (gb == b) mine = r;
         }
+        dest = mine != 0xffffffffu ? __ldg(g.area + mine) + sub : t - excess;
     }
-    if (dirty) store_xyzz(partials + seg, acc);
+    store_xyzz(partials + dest, acc);
 }
 
-// Thread-per-bucket finish pass, for MANY buckets with few partials each: with more buckets than resident quads the pass is
-// throughput-bound and the quad-cooperative variant below only adds work.  run == 0: the bucket's partials are summed one by
-// one; run > 0: k_run_sum ran first and the bucket's value is spread over its first slot and the multiples of `run` inside it.
-template <class F>
-__global__ void __launch_bounds__(128) k_bucket_finish_serial(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
-                                                              uint32_t K, uint32_t smax, const uint32_t* __restrict__ meta, uint32_t run, xyzz_t* buckets,
-                                                              const xyzz_t* __restrict__ partials) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    const uint32_t nbk = __ldg(offsets + b + 1) - __ldg(offsets + b);
-    uint32_t sb = (nbk + K - 1) / K;
-    if (sb > smax && meta[2] <= MSM_MAX_GIANTS) return;  // k_giant_finish
-    if (sb < 2) return;                                  // 0: empty, 1: written by k_accumulate
-    const uint32_t a = __ldg(task_off + b);
-    xyzz_t acc = load_xyzz(partials + a);
-    if (run == 0) {
-        for (uint32_t j = 1; j < sb; j++) acc = xyzz_add<F, true>(acc, load_xyzz(partials + a + j));
-    } else {
-        for (uint32_t k = (a / run + 1) * run; k < a + sb; k += run) acc = xyzz_add<F, true>(acc, load_xyzz(partials + k));
-    }
-    store_xyzz(buckets + b, acc);
-}
-
-// Buckets with 2 <= s_b <= smax tasks: a group of G = 2^log_g QUADS (quad.cuh) sums the bucket's partials — strided serial
-// part, then a shuffle tree over the quads of the group.  One quad per bucket when buckets hold only a few partials.
-template <class F>
-__global__ void __launch_bounds__(128) k_bucket_finish(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
-                                                       uint32_t K, uint32_t smax, unsigned log_g, const uint32_t* __restrict__ meta,
-                                                       xyzz_t* buckets, const xyzz_t* __restrict__ partials) {
-    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // global quad
-    const uint32_t G = 1u << log_g, b = gq >> log_g, gl = gq & (G - 1);
-    uint32_t sb = 0, t0 = 0;
-    if (b < nb) {
-        const uint32_t nbk = __ldg(offsets + b + 1) - __ldg(offsets + b);
-        sb = (nbk + K - 1) / K;
-        t0 = __ldg(task_off + b);
-        // giants are left to k_giant_finish — unless their list overflowed, then they are summed here (slow, correct)
-        if (sb > smax && meta[2] <= MSM_MAX_GIANTS) sb = 0;
-        if (sb < 2) sb = 0;
-    }
-    // warp-uniform trip count: every lane must take part in the quad additions' shuffles
-    const unsigned my_trips = sb > gl ? (sb - gl + G - 1) / G : 0;
-    const unsigned trips = __reduce_max_sync(0xffffffffu, my_trips);
-    xyzz_t acc = xyzz_identity();
-    for (unsigned k = 0; k < trips; k++) {
-        const uint32_t j = gl + k * G;
-        xyzz_t o = j < sb ? load_xyzz(partials + t0 + j) : xyzz_identity();
-        acc = xyzz_add_quad<F>(acc, o);
-    }
-#pragma unroll 1
-    for (unsigned d = G >> 1; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
-        if (gl >= d) o = xyzz_identity();
-        acc = xyzz_add_quad<F>(acc, o);
-    }
-    if (gl == 0 && sb && (threadIdx.x & 3) == 0) store_xyzz(buckets + b, acc);
-}
-
-// ---------------------------------------------------------------------------------------------- bucket reduction
-// sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of (b+1) set.
-// grid (blocks_per_bit, c, G); every CTA tree-sums its slice of one group's buckets for one bit.
-constexpr unsigned TREE_THREADS = 256;              // 64 quads per CTA in the reduction kernels
+// ---------------------------------------------------------------------------------------------- sums of partials
+constexpr unsigned TREE_THREADS = 256;              // 64 quads per CTA in the giant / final kernels
 constexpr unsigned TREE_QUADS = TREE_THREADS / 4;
+constexpr unsigned ROWCOL_THREADS = 128;            // 32 quads per row / column CTA: the whole grid of a single MSM is one wave
 
-// GIANT_SLICES CTAs per giant bucket: each sums a contiguous slice of the bucket's partial list (quads stride over it, then
-// the block tree, quad.cuh); the last CTA to arrive (ticket counter) adds the slice sums and writes the bucket.
-constexpr unsigned GIANT_SLICES = 16;
+// Block-wide sum of one value per QUAD (replicated in its four lanes; quad.cuh): three shuffle levels inside every warp, one
+// shared-memory hand-over, then the warps' sums in warp 0.  One barrier instead of one per level.  blockDim.x a multiple of 32,
+// <= 1024; sm holds blockDim.x / 32 points.  Result valid in quad 0 of warp 0.
+template <class F> __device__ __forceinline__ xyzz_t block_sum_quads(xyzz_t acc, xyzz_t* sm) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, qw = lane >> 2, wid = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll 1
+    for (unsigned d = 4; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
+        if (qw >= d) o = xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    if (nw == 1) return acc;
+    if (lane == 0) store_xyzz(sm + wid, acc);
+    __syncthreads();
+    if (wid != 0) return acc;
+    acc = qw < nw ? load_xyzz(sm + qw) : xyzz_identity();
+    unsigned top = 1;
+    while (top < nw) top <<= 1;      // nw <= 8 here; a 32-warp block would need a second hand-over
+#pragma unroll 1
+    for (unsigned d = top >> 1; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
+        if (qw >= d) o = xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    return acc;
+}
+
+// GIANT_SLICES CTAs per listed giant bucket: each sums a contiguous slice of the giant's side area (quads stride over it, then
+// the block sum); the last CTA to arrive (ticket counter) adds the slice sums and writes the giant's main slot.
+constexpr unsigned GIANT_SLICES = 16, GIANT_GRID = 32;
 template <class F>
 __global__ void __launch_bounds__(TREE_THREADS) k_giant_finish(const uint32_t* __restrict__ giants, const uint32_t* __restrict__ meta,
-                                                               const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t K,
-                                                               xyzz_t* buckets, const xyzz_t* __restrict__ partials, xyzz_t* slice_sums,
+                                                               const uint32_t* __restrict__ task_off, xyzz_t* partials, xyzz_t* slice_sums,
                                                                uint32_t* tickets) {
-    extern __shared__ xyzz_t sm_tree[];
+    __shared__ xyzz_t sm_tree[TREE_THREADS / 32];
     __shared__ uint32_t ticket_s;
-    const uint32_t ng = meta[2];
-    if (ng > MSM_MAX_GIANTS || blockIdx.x >= ng) return;  // overflow: k_bucket_finish took them
-    const uint32_t b = giants[blockIdx.x];
-    const uint32_t nbk = offsets[b + 1] - offsets[b], sb = (nbk + K - 1) / K, t0 = task_off[b];
-    const uint32_t per = (sb + GIANT_SLICES - 1) / GIANT_SLICES;
-    const uint32_t j_lo = blockIdx.y * per, j_hi = min(sb, j_lo + per);
+    const GiantList g = giant_list(meta, giants);
     const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
-    xyzz_t acc = xyzz_identity();
-    for (uint32_t j0 = j_lo; j0 < j_hi; j0 += nq) {
-        xyzz_t o = j0 + qd < j_hi ? load_xyzz(partials + t0 + j0 + qd) : xyzz_identity();
-        acc = xyzz_add_quad<F>(acc, o);
-    }
-    acc = block_tree_sum_quad<F>(acc, sm_tree);
-    xyzz_t* mine = slice_sums + (size_t)blockIdx.x * GIANT_SLICES;
-    if (threadIdx.x == 0) {
-        store_xyzz(mine + blockIdx.y, acc);
-        __threadfence();
-        ticket_s = atomicAdd(&tickets[blockIdx.x], 1u);
-    }
-    __syncthreads();
-    if (ticket_s != GIANT_SLICES - 1) return;
-    __threadfence();
-    acc = qd < GIANT_SLICES ? load_xyzz(mine + qd) : xyzz_identity();
-    acc = block_tree_sum_quad<F>(acc, sm_tree);
-    if (threadIdx.x == 0) { store_xyzz(buckets + b, acc); tickets[blockIdx.x] = 0; }
-}
-
-// sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of i = b+1 set, i in [1, B], B = 2^(c-1).
-// For t < c-1 exactly B/2 indices qualify; the j-th is i = (j >> t) << (t+1) | 1 << t | (j & (2^t - 1)).  Slice c-1 is the
-// single bucket i = B.  grid (blocks_per_bit, c-1, G): every CTA sums a contiguous range of j, a few per quad, then the
-// block tree.
-template <class F>
-__global__ void __launch_bounds__(TREE_THREADS) k_bitsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned c, xyzz_t* partial) {
-    extern __shared__ xyzz_t sm_tree[];
-    const unsigned t = blockIdx.y, g = blockIdx.z, nblk = gridDim.x;
-    const uint32_t half = B >> 1, per = (half + nblk - 1) / nblk;
-    const uint32_t j0 = blockIdx.x * per, j1 = min(half, j0 + per);
-    const xyzz_t* bk = buckets + (size_t)g * B;
-    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
-    xyzz_t acc = xyzz_identity();
-    for (uint32_t jb = j0; jb < j1; jb += nq) {
-        const uint32_t j = jb + qd;
-        xyzz_t o = xyzz_identity();
-        if (j < j1) {
-            uint32_t i = ((j >> t) << (t + 1)) | (1u << t) | (j & ((1u << t) - 1));
-            o = load_xyzz(bk + (i - 1));
-        }
-        acc = xyzz_add_quad<F>(acc, o);
-    }
-    acc = block_tree_sum_quad<F>(acc, sm_tree);
-    if (threadIdx.x == 0) store_xyzz(partial + ((size_t)g * c + t) * nblk + blockIdx.x, acc);
-}
-
-// second stage: one small CTA per (group, bit) sums the CTA partials; bit c-1 is copied from its bucket.
-template <class F>
-__global__ void __launch_bounds__(64) k_bitsum_final(const xyzz_t* __restrict__ partial, const xyzz_t* __restrict__ buckets, uint32_t B, unsigned c,
-                                                     unsigned nblk, xyzz_t* out) {
-    extern __shared__ xyzz_t sm_tree[];
-    const unsigned g = blockIdx.x / c, t = blockIdx.x % c;
-    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
-    xyzz_t acc = xyzz_identity();
-    if (t == c - 1) {
-        if (qd == 0) acc = load_xyzz(buckets + (size_t)g * B + (B - 1));
-    } else {
-        for (unsigned j0 = 0; j0 < nblk; j0 += nq) {
-            xyzz_t o = j0 + qd < nblk ? load_xyzz(partial + (size_t)blockIdx.x * nblk + j0 + qd) : xyzz_identity();
+    for (uint32_t r = blockIdx.x; r < g.ng; r += gridDim.x) {
+        const uint32_t sb = __ldg(g.tasks + r), t0 = __ldg(g.area + r);
+        const uint32_t per = (sb + GIANT_SLICES - 1) / GIANT_SLICES;
+        const uint32_t j_lo = min(sb, blockIdx.y * per), j_hi = min(sb, j_lo + per);
+        xyzz_t acc = xyzz_identity();
+        for (uint32_t j0 = j_lo; j0 < j_hi; j0 += nq) {
+            xyzz_t o = j0 + qd < j_hi ? load_xyzz(partials + t0 + j0 + qd) : xyzz_identity();
             acc = xyzz_add_quad<F>(acc, o);
         }
-    }
-    acc = block_tree_sum_quad<F>(acc, sm_tree);
-    if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, acc);
-}
-
-// Two-level form of the same reduction (fewer additions, shorter dependency chains).  Split i = hi * W + lo, W = 2^w_lo:
-//     sum_i i * B[i] = W * sum_hi hi * R[hi] + sum_lo lo * C[lo],   R[hi] = sum_lo B[hi W + lo],  C[lo] = sum_hi B[hi W + lo]
-// k_gridsum: one CTA per row and per column of the (B/W + 1) x W bucket grid (row B/W holds the single bucket i = B);
-// k_gridsum_final: one CTA per output bit: T_t = sum of C[lo] over bit t of lo (t < w_lo), of R[hi] over bit t - w_lo of hi
-// (t >= w_lo).  Output layout and meaning are those of k_bitsum_final: c points per group, the MSM is sum_t 2^t T_t.
-// About 2 B additions per group instead of (c - 1) B / 2.
-template <class F>
-__global__ void __launch_bounds__(TREE_THREADS) k_gridsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned w_lo, xyzz_t* rc) {
-    extern __shared__ xyzz_t sm_tree[];
-    const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
-    const unsigned g = blockIdx.z;
-    const xyzz_t* bk = buckets + (size_t)g * B;
-    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
-    const bool row = blockIdx.x < nrows;
-    const uint32_t fixed = row ? blockIdx.x : blockIdx.x - nrows, count = row ? W : nrows;
-    xyzz_t acc = xyzz_identity();
-    for (uint32_t e0 = 0; e0 < count; e0 += nq) {
-        const uint32_t e = e0 + qd;
-        xyzz_t o = xyzz_identity();
-        if (e < count) {
-            const uint32_t i = row ? fixed * W + e : e * W + fixed;
-            if (i >= 1 && i <= B) o = load_xyzz(bk + (i - 1));
+        acc = block_sum_quads<F>(acc, sm_tree);
+        xyzz_t* mine = slice_sums + (size_t)r * GIANT_SLICES;
+        if (threadIdx.x == 0) {
+            store_xyzz(mine + blockIdx.y, acc);
+            __threadfence();
+            ticket_s = atomicAdd(&tickets[r], 1u);
         }
-        acc = xyzz_add_quad<F>(acc, o);
+        __syncthreads();
+        if (ticket_s == GIANT_SLICES - 1) {
+            __threadfence();
+            acc = qd < GIANT_SLICES ? load_xyzz(mine + qd) : xyzz_identity();
+            __syncthreads();   // sm_tree is reused
+            acc = block_sum_quads<F>(acc, sm_tree);
+            if (threadIdx.x == 0) { store_xyzz(partials + slot_of(task_off, __ldg(g.bucket + r), g), acc); tickets[r] = 0; }
+        }
+        __syncthreads();
     }
-    acc = block_tree_sum_quad<F>(acc, sm_tree);
-    if (threadIdx.x == 0) store_xyzz(rc + (size_t)g * (nrows + W) + blockIdx.x, acc);
 }
 
+// Row and column sums of the (B/W + 1) x W grid of bucket weights i = b + 1 = hi * W + lo, W = 2^w_lo, straight from the
+// partial list:   sum_i i * B[i] = W * sum_hi hi * R[hi] + sum_lo lo * C[lo],   R[hi] = sum of the partials of row hi's buckets (one
+// contiguous slot range), C[lo] = sum of the partials of the buckets hi * W + lo over hi (their slot ranges walked as one flat
+// list, so the quads of a CTA share the work evenly whatever the bucket sizes).  One CTA per row and per column and group;
+// about 2 additions per partial in total, <= ceil(slots / quads) dependent additions per quad plus the block sum.
+constexpr unsigned ROWCOL_MAX_ROWS = 260;           // B / W + 1 <= 257 for c <= 17
 template <class F>
-__global__ void __launch_bounds__(TREE_THREADS) k_gridsum_final(const xyzz_t* __restrict__ rc, uint32_t B, unsigned w_lo, unsigned c, xyzz_t* out) {
-    extern __shared__ xyzz_t sm_tree[];
+__global__ void __launch_bounds__(ROWCOL_THREADS) k_rowcol(const xyzz_t* __restrict__ partials, const uint32_t* __restrict__ task_off,
+                                                           const uint32_t* __restrict__ meta, const uint32_t* __restrict__ giants, uint32_t B,
+                                                           unsigned w_lo, xyzz_t* rc) {
+    __shared__ xyzz_t sm_tree[ROWCOL_THREADS / 32];
+    __shared__ uint32_t s_start[ROWCOL_MAX_ROWS], s_pref[ROWCOL_MAX_ROWS + 1];
+    __shared__ uint32_t s_warp[ROWCOL_THREADS / 32];
+    const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
+    const unsigned g = blockIdx.z, tid = threadIdx.x, qd = tid >> 2, nq = blockDim.x >> 2;
+    const uint32_t gb0 = g * B;
+    const GiantList gl = giant_list(meta, giants);
+    xyzz_t acc = xyzz_identity();
+    if (blockIdx.x < nrows) {
+        const uint32_t hi = blockIdx.x;
+        const uint32_t i_first = max(hi * W, 1u), i_last = min(hi * W + W - 1, B);
+        const uint32_t s0 = slot_of(task_off, gb0 + i_first - 1, gl), s1 = slot_of(task_off, gb0 + i_last, gl);
+        // software pipeline: the next partial is in flight while the current one is added
+        xyzz_t cur = s0 + qd < s1 ? load_xyzz(partials + s0 + qd) : xyzz_identity();
+        for (uint32_t s = s0; s < s1; s += nq) {
+            const uint32_t nx = s + nq + qd;
+            xyzz_t nxt = nx < s1 ? load_xyzz(partials + nx) : xyzz_identity();
+            acc = xyzz_add_quad<F>(acc, cur);
+            cur = nxt;
+        }
+    } else {
+        const uint32_t lo = blockIdx.x - nrows;
+        // slot range of every bucket of the column, then an exclusive scan of the range lengths (nrows <= 3 * blockDim.x)
+        uint32_t cnt[3], mysum = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 3; k++) {
+            const uint32_t hi = tid * 3 + k;
+            cnt[k] = 0;
+            if (hi < nrows) {
+                const uint32_t i = hi * W + lo;
+                uint32_t st = 0;
+                if (i >= 1 && i <= B) {
+                    st = slot_of(task_off, gb0 + i - 1, gl);
+                    cnt[k] = slot_of(task_off, gb0 + i, gl) - st;
+                }
+                s_start[hi] = st;
+            }
+            mysum += cnt[k];
+        }
+        uint32_t x = mysum;
+        const unsigned lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (unsigned)d) x += y;
+        }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (unsigned k = 0; k < wid; k++) wbase += s_warp[k];
+        uint32_t ex = wbase + x - mysum;
+#pragma unroll
+        for (unsigned k = 0; k < 3; k++) {
+            const uint32_t hi = tid * 3 + k;
+            if (hi < nrows) s_pref[hi] = ex;
+            ex += cnt[k];
+        }
+        if (tid == blockDim.x - 1) s_pref[nrows] = ex;
+        __syncthreads();
+        const uint32_t total = s_pref[nrows];
+        auto fetch = [&](uint32_t f) -> xyzz_t {
+            if (f >= total) return xyzz_identity();
+            uint32_t l = 0, h = nrows;      // s_pref[l] <= f < s_pref[h]
+            while (h - l > 1) {
+                const uint32_t m = (l + h) >> 1;
+                if (s_pref[m] <= f) l = m; else h = m;
+            }
+            return load_xyzz(partials + s_start[l] + (f - s_pref[l]));
+        };
+        xyzz_t cur = fetch(qd);
+        for (uint32_t f0 = 0; f0 < total; f0 += nq) {
+            xyzz_t nxt = fetch(f0 + nq + qd);
+            acc = xyzz_add_quad<F>(acc, cur);
+            cur = nxt;
+        }
+    }
+    acc = block_sum_quads<F>(acc, sm_tree);
+    if (tid == 0) store_xyzz(rc + (size_t)g * (nrows + W) + blockIdx.x, acc);
+}
+
+// One CTA per output bit and group: T_t = sum of C[lo] over bit t of lo (t < w_lo), of R[hi] over bit t - w_lo of hi (t >= w_lo).
+// c points per group; the group's value is sum_t 2^t T_t (finished on the host: c doublings).
+template <class F>
+__global__ void __launch_bounds__(TREE_THREADS) k_bit_slices(const xyzz_t* __restrict__ rc, uint32_t B, unsigned w_lo, unsigned c, xyzz_t* out) {
+    __shared__ xyzz_t sm_tree[TREE_THREADS / 32];
     const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
     const unsigned t = blockIdx.x, g = blockIdx.y;
     const bool cols = t < w_lo;
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(TREE_THREADS) k_gridsum_final(const xyzz_t* __
         xyzz_t o = e < count ? load_xyzz(src + e) : xyzz_identity();
         acc = xyzz_add_quad<F>(acc, o);
     }
-    acc = block_tree_sum_quad<F>(acc, sm_tree);
+    acc = block_sum_quads<F>(acc, sm_tree);
     if (threadIdx.x == 0) store_xyzz(out + (size_t)g * c + t, acc);
 }
 
@@ -474,69 +478,58 @@ static void free_dev(void* p) { if (p) cudaFree(p); }
 
 void msm_workspace_free(MsmWorkspace& ws) {
     free_dev(ws.d_digits); free_dev(ws.d_entries); free_dev(ws.d_partials);
-    free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_buckets);
+    free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_chain); free_dev(ws.d_chain_flag);
     free_dev(ws.d_bitsums); free_dev(ws.d_meta); free_dev(ws.d_giants); free_dev(ws.d_giant_slices); free_dev(ws.d_giant_tickets);
     if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
     for (auto& e : ws.ev) if (e) cudaEventDestroy(e);
     ws = MsmWorkspace();
 }
 
-static unsigned pow2_ceil_log(uint64_t x) {
-    unsigned l = 0;
-    while (((uint64_t)1 << l) < x) l++;
-    return l;
-}
-
 template <class F, class FS>
-int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, bool scalars_mont, unsigned c, MsmWorkspace& ws,
-            cudaStream_t st, MsmResultShape* shape, unsigned* launches) {
+int msm_run(const MsmBases& b, size_t off, size_t n, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
+            MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches) {
     if (off > b.n || n > b.n - off) { zk_set_error("msm: slice [%zu, %zu) outside the %zu resident bases", off, off + n, b.n); return ZK_ERR_INVALID; }
-    shape->c = 0; shape->groups = 0;
+    if (k == 0 || k > MSM_MAX_BATCH) { zk_set_error("msm: batch of %u outside [1, %u]", k, MSM_MAX_BATCH); return ZK_ERR_INVALID; }
+    shape->c = 0; shape->groups = 0; shape->batch = k;
     if (n == 0) return ZK_OK;
     const bool use_table = b.c != 0;
     if (use_table) c = b.c;
     else if (c == 0) c = (unsigned)msm_default_window(n, false);
     if (c < 2 || c > MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window bits %u outside [2, %u]", c, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
     const unsigned nwin = msm_num_windows(c);
-    const unsigned G = use_table ? 1 : nwin;          // bucket groups
+    const unsigned gpm = use_table ? 1 : nwin;        // bucket groups per MSM
+    const unsigned G = k * gpm;                       // bucket groups of the batch
     const uint32_t B = 1u << (c - 1);                 // buckets per group
     const size_t NB = (size_t)G * B;
-    const size_t Mmax = n * nwin;
-    if (Mmax >= 0x7fffffffull || b.n * (size_t)std::max(1u, b.nwin) >= 0x7fffffffull) { zk_set_error("msm: %zu x %u entries exceed the 31-bit index space", n, nwin); return ZK_ERR_INVALID; }
-    // Entries per accumulation task: the accumulate kernel keeps `capacity` threads resident (4 CTAs of 128 per SM at
-    // <= 128 registers); K is chosen so that the tasks fill a whole number of waves (a 1.02-wave grid costs two waves).
-    const size_t capacity = (size_t)ws.sm_count * 512;
-    const size_t resident_quads = (size_t)ws.sm_count * TREE_QUADS;
-    const bool many_buckets = NB > resident_quads;    // many small buckets: throughput regime (see k_bucket_finish_serial)
-    const bool serial_finish = ws.finish_mode == 0 ? many_buckets : ws.finish_mode == 1;
+    const size_t Mmax = n * nwin * (size_t)k;
+    if (Mmax >= 0x7fffffffull || NB >= 0x7fffffffull || b.n * (size_t)std::max(1u, b.nwin) >= 0x7fffffffull) {
+        zk_set_error("msm: %zu x %u x %u entries exceed the 31-bit index space", n, nwin, k);
+        return ZK_ERR_INVALID;
+    }
+    // Entries per accumulation task: the tasks fill the machine ONCE (wave_threads accumulation threads per SM; the mixed
+    // addition rate saturates from ~8 warps per SM, tools/microbench.py) — every further task is one more partial for the
+    // latency-bound reduction behind the accumulation.  Very large inputs get several waves of <= 256-entry tasks.
+    const size_t wave_threads = ws.wave_threads ? ws.wave_threads : 384;
+    const size_t capacity = (size_t)ws.sm_count * wave_threads;
     uint32_t K = ws.chunk;
     if (K == 0) {
         const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
-        size_t waves = (Mmax + 64 * capacity - 1) / (64 * capacity);   // long tasks for large inputs: fewer partials to sum
+        size_t waves = (Mmax + 256 * capacity - 1) / (256 * capacity);
         if (waves == 0) waves = 1;
-        // a cheap finish pass affords twice as many (half as long, better balanced) tasks
-        if (many_buckets && Mmax / (2 * waves * capacity) >= 6) waves *= 2;
         K = (uint32_t)((Mmax + waves * capacity - slack - 1) / (waves * capacity - slack));
         if (K < 4) K = 4;
     }
     const size_t NTmax = Mmax / K + NB + 1;           // sum_b ceil(n_b / K) <= M / K + (number of non-empty buckets)
-    // lanes per bucket in the finish pass: ~a quarter of the expected partials per bucket
-    const uint64_t s_avg = Mmax / ((uint64_t)K * NB) + 1;
-    unsigned log_g = pow2_ceil_log((s_avg + 7) / 8);   // quads per bucket in the finish pass
-    if (log_g > 3) log_g = 3;
-    const uint32_t smax = 32u << log_g;               // more partials than this: the bucket is "giant"
-    // bit-sliced bucket sums: (c-1) slices of B/2 elements; elements per quad chosen so that all CTAs are resident at once
-    unsigned bs_threads = TREE_THREADS;
-    while (bs_threads > 32 && bs_threads / 4 > B / 2) bs_threads /= 2;
-    size_t per_quad = ((size_t)(c - 1) * (B / 2) * G + resident_quads - 1) / resident_quads;
-    if (per_quad < 2) per_quad = 2;
-    unsigned nblk = 1;
-    while (nblk < 64 && (size_t)nblk * 2 * (bs_threads / 4) * per_quad <= B / 2) nblk *= 2;
+    const uint32_t smax = 8 * (ROWCOL_THREADS / 4);   // more partials than this in one bucket: "giant" (side area + k_giant_finish)
+    const unsigned w_lo = (c - 1) / 2;
+    const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
+    const size_t ntiles = (NB + PLAN_TILE - 1) / PLAN_TILE;
 
     static_assert(sizeof(xyzz_t) == 128 && sizeof(affine_t) == 64 && sizeof(fe) == 32, "layout");
-    // scratch, grouped by what sizes it: the entry list (n * nwin), the bucket array (G * B), the bit sums (G * c)
+    if (nrows > ROWCOL_MAX_ROWS || nrows > 3 * ROWCOL_THREADS) { zk_set_error("msm: window %u has too many bucket rows", c); return ZK_ERR_INVALID; }
+    // scratch, grouped by what sizes it: the entry list (k * n * nwin), the bucket counters (G * B), the slice sums (G * c)
     {
-        const size_t need_entries = Mmax * sizeof(uint32_t), need_partials = NTmax * sizeof(xyzz_t);
+        const size_t need_entries = Mmax * sizeof(uint32_t), need_partials = (NTmax + MSM_MAX_GIANTS) * sizeof(xyzz_t);
         if (ws.cap_entries < need_entries) {
             free_dev(ws.d_digits); free_dev(ws.d_entries);
             ws.d_digits = nullptr; ws.d_entries = nullptr; ws.cap_entries = 0;
@@ -551,17 +544,18 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
             ws.cap_partials = need_partials;
         }
         if (ws.cap_buckets < NB) {
-            free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_buckets);
-            ws.d_counts = ws.d_offsets = ws.d_task_off = nullptr; ws.d_buckets = nullptr; ws.cap_buckets = 0;
+            free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_chain); free_dev(ws.d_chain_flag);
+            ws.d_counts = ws.d_offsets = ws.d_task_off = ws.d_chain_flag = nullptr; ws.d_chain = nullptr; ws.cap_buckets = 0;
             ZK_CUDA(cudaMalloc(&ws.d_counts, NB * sizeof(uint32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_offsets, (NB + 1) * sizeof(uint32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_task_off, (NB + 1) * sizeof(uint32_t)));
-            ZK_CUDA(cudaMalloc(&ws.d_buckets, NB * sizeof(xyzz_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_chain, ntiles * sizeof(uint64_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_chain_flag, ntiles * sizeof(uint32_t)));
+            ZK_CUDA(cudaMemsetAsync(ws.d_chain_flag, 0, ntiles * sizeof(uint32_t), st));
+            ws.epoch = 0;
             ws.cap_buckets = NB;
         }
-        const unsigned w_lo = (c - 1) / 2;
-        const size_t grid_pts = (size_t)G * (((size_t)B >> w_lo) + 1 + ((size_t)1 << w_lo));
-        const size_t need_bits = std::max((size_t)G * c * (nblk + 1), grid_pts + (size_t)G * c);
+        const size_t need_bits = (size_t)G * (nrows + W) + (size_t)G * c;
         if (ws.cap_bits < need_bits) {
             free_dev(ws.d_bitsums);
             ws.d_bitsums = nullptr; ws.cap_bits = 0;
@@ -576,8 +570,8 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
             ws.cap_hbits = (size_t)G * c;
         }
         if (!ws.d_meta) {
-            ZK_CUDA(cudaMalloc(&ws.d_meta, 4 * sizeof(uint32_t)));
-            ZK_CUDA(cudaMalloc(&ws.d_giants, MSM_MAX_GIANTS * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_meta, 8 * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_giants, 3 * MSM_MAX_GIANTS * sizeof(uint32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_giant_slices, (size_t)MSM_MAX_GIANTS * GIANT_SLICES * sizeof(xyzz_t)));
             ZK_CUDA(cudaMalloc(&ws.d_giant_tickets, MSM_MAX_GIANTS * sizeof(uint32_t)));
             ZK_CUDA(cudaMemsetAsync(ws.d_giant_tickets, 0, MSM_MAX_GIANTS * sizeof(uint32_t), st));
@@ -585,81 +579,56 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, boo
     }
     unsigned nl = 0;
     if (ws.profile && !ws.ev[0])
-        for (int k = 0; k <= MSM_ST_COUNT; k++) ZK_CUDA(cudaEventCreate(&ws.ev[k]));
-#define STAGE_MARK(k) do { if (ws.profile) ZK_CUDA(cudaEventRecord(ws.ev[k], st)); } while (0)
+        for (int s = 0; s <= MSM_ST_COUNT; s++) ZK_CUDA(cudaEventCreate(&ws.ev[s]));
+#define STAGE_MARK(s) do { if (ws.profile) ZK_CUDA(cudaEventRecord(ws.ev[s], st)); } while (0)
 
+    MsmScalarSet sc{};
+    for (unsigned j = 0; j < k; j++) sc.p[j] = d_scalars[j];
+    const uint32_t epoch = ++ws.epoch;
     ZK_CUDA(cudaMemsetAsync(ws.d_counts, 0, NB * sizeof(uint32_t), st));
-    ZK_CUDA(cudaMemsetAsync(ws.d_buckets, 0, NB * sizeof(xyzz_t), st));  // all-zero XYZZ == identity
     STAGE_MARK(0);
     // 1. digits + histogram
-    k_recode<FS><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_scalars_in, scalars_mont ? 1 : 0, n, c, nwin, use_table ? 0 : 1, ws.d_digits, ws.d_counts);
+    k_recode<FS><<<dim3((unsigned)((n + 127) / 128), k), 128, 0, st>>>(sc, scalars_mont ? 1 : 0, n, c, nwin, gpm, use_table ? 0 : 1, ws.d_digits,
+                                                                        ws.d_counts, ws.d_meta);
     STAGE_MARK(1);
-    // 2. plan: bucket offsets, task offsets, giant list
-    k_plan<<<1, 1024, 0, st>>>(ws.d_counts, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, ws.d_giants);
+    // 2. plan: bucket offsets, task offsets, giant list and side areas
+    k_plan<<<(unsigned)ntiles, 1024, 0, st>>>(ws.d_counts, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, ws.d_giants, ws.d_chain,
+                                               ws.d_chain_flag, epoch);
     STAGE_MARK(2);
     // 3. scatter (counting sort by bucket)
-    k_scatter<<<(unsigned)((Mmax + 255) / 256), 256, 0, st>>>(ws.d_digits, n, c, nwin, use_table ? 0 : 1, off, b.n, use_table ? 1 : 0,
+    k_scatter<<<(unsigned)((Mmax + 255) / 256), 256, 0, st>>>(ws.d_digits, n, c, nwin, k, gpm, use_table ? 0 : 1, off, b.n, use_table ? 1 : 0,
                                                             ws.d_offsets, ws.d_counts, ws.d_entries);
     STAGE_MARK(3);
     // 4. accumulation: one task per <= K sorted entries of one bucket
     k_accumulate<F><<<(unsigned)((NTmax + 127) / 128), 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, ws.d_meta,
-                                                                   ws.d_buckets, ws.d_partials);
+                                                                   ws.d_giants, ws.d_partials);
     STAGE_MARK(4);
-    // 5. per-bucket sums of the task partials (+ giants)
-    // giants first: k_giant_finish reads the untouched partial lists, k_run_sum then rewrites partials in place
-    k_giant_finish<F><<<dim3(MSM_MAX_GIANTS, GIANT_SLICES), TREE_THREADS, TREE_QUADS * sizeof(xyzz_t), st>>>(
-        ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials, ws.d_giant_slices, ws.d_giant_tickets);
-    if (serial_finish) {
-        const uint32_t run = ws.run_len;
-        if (run) {
-            const size_t threads = (NTmax + run - 1) / run;
-            k_run_sum<F><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ws.d_task_off, (uint32_t)NB, ws.d_meta, run, smax, ws.d_partials);
-            nl += 1;
-        }
-        k_bucket_finish_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, run, ws.d_buckets, ws.d_partials);
-    } else {
-        k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
-                                                                                  ws.d_buckets, ws.d_partials);
-    }
+    // 5. giants to one slot each, then row / column sums straight from the partial list
+    k_giant_finish<F><<<dim3(GIANT_GRID, GIANT_SLICES), TREE_THREADS, 0, st>>>(ws.d_giants, ws.d_meta, ws.d_task_off, ws.d_partials, ws.d_giant_slices,
+                                                                                 ws.d_giant_tickets);
+    xyzz_t* d_rc = ws.d_bitsums;
+    xyzz_t* d_T = ws.d_bitsums + (size_t)G * (nrows + W);
+    k_rowcol<F><<<dim3(nrows + W, 1, G), ROWCOL_THREADS, 0, st>>>(ws.d_partials, ws.d_task_off, ws.d_meta, ws.d_giants, B, w_lo, d_rc);
     STAGE_MARK(5);
-    // 6. bit-sliced bucket sums
-    xyzz_t* d_partial = ws.d_bitsums;
-    xyzz_t* d_T;
-    if (ws.reduce_mode == 0) {
-        d_T = ws.d_bitsums + (size_t)G * c * nblk;
-        if (c > 1 && B >= 2)
-            k_bitsum<F><<<dim3(nblk, c - 1, G), bs_threads, (bs_threads / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, c, d_partial);
-        k_bitsum_final<F><<<G * c, 64, 16 * sizeof(xyzz_t), st>>>(d_partial, ws.d_buckets, B, c, nblk, d_T);
-    } else {
-        const unsigned w_lo = (c - 1) / 2;
-        const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
-        d_T = ws.d_bitsums + (size_t)G * (nrows + W);
-        // a quad per 1-2 elements of a row / column, but never more CTAs x threads than are resident at once (the kernels
-        // need ~190 registers: 320 threads per SM), so that the whole grid runs as one wave
-        unsigned gt = TREE_THREADS;
-        while (gt > 32 && (gt / 4 >= 2 * std::max(W, nrows) || (size_t)G * (nrows + W) * gt > (size_t)ws.sm_count * 320)) gt /= 2;
-        k_gridsum<F><<<dim3(nrows + W, 1, G), gt, (gt / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, w_lo, d_partial);
-        unsigned ft = TREE_THREADS;                 // half of the elements carry a given bit
-        while (ft > 32 && ft / 4 >= std::max(W, nrows)) ft /= 2;
-        k_gridsum_final<F><<<dim3(c, G), ft, (ft / 4) * sizeof(xyzz_t), st>>>(d_partial, B, w_lo, c, d_T);
-    }
-    nl += 8;
+    // 6. bit slices of the row / column sums
+    unsigned ft = TREE_THREADS;                 // half of the elements carry a given bit
+    while (ft > 32 && ft / 4 >= std::max(W, nrows)) ft /= 2;
+    k_bit_slices<F><<<dim3(c, G), ft, 0, st>>>(d_rc, B, w_lo, c, d_T);
+    nl += 7;
     STAGE_MARK(6);
     ZK_CUDA(cudaGetLastError());
+    shape->c = c; shape->groups = gpm;
+    if (launches) *launches += nl;
     if (ws.d_T_out) {
         if ((size_t)G * c > ws.d_T_cap) { zk_set_error("msm: %u slice sums do not fit the caller's buffer of %zu points", G * c, ws.d_T_cap); return ZK_ERR_INVALID; }
         ZK_CUDA(cudaMemcpyAsync(ws.d_T_out, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToDevice, st));
-        shape->c = c; shape->groups = G;
-        if (launches) *launches += nl;
         return ZK_OK;
     }
-    ZK_CUDA(cudaMemcpyAsync(ws.h_bitsums + (size_t)(ws.h_slot & 1) * G * c, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
-    shape->c = c; shape->groups = G;
-    if (launches) *launches += nl;
+    ZK_CUDA(cudaMemcpyAsync(ws.h_bitsums + (size_t)(ws.h_slot & 1) * ws.cap_hbits, d_T, (size_t)G * c * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     if (ws.defer_sync) return ZK_OK;
     ZK_CUDA(cudaStreamSynchronize(st));
     if (ws.profile)
-        for (int k = 0; k < MSM_ST_COUNT; k++) ZK_CUDA(cudaEventElapsedTime(&ws.stage_ms[k], ws.ev[k], ws.ev[k + 1]));
+        for (int s = 0; s < MSM_ST_COUNT; s++) ZK_CUDA(cudaEventElapsedTime(&ws.stage_ms[s], ws.ev[s], ws.ev[s + 1]));
 #undef STAGE_MARK
     // the O(c) serial tail (c doublings per group) is finished on the host from ws.h_bitsums (api.cu: msm_finish)
     return ZK_OK;
@@ -692,7 +661,7 @@ template int msm_sum_partials<FqParams>(const xyzz_t*, size_t, size_t, xyzz_t*, 
 
 #define INST(F, FS)                                                                                                             \
     template int msm_bases_create<F>(MsmBases&, const affine_t*, bool, size_t, unsigned, cudaStream_t);                          \
-    template int msm_run<F, FS>(const MsmBases&, size_t, size_t, const fe*, bool, unsigned, MsmWorkspace&, cudaStream_t, MsmResultShape*, unsigned*);
+    template int msm_run<F, FS>(const MsmBases&, size_t, size_t, const fe* const*, unsigned, bool, unsigned, MsmWorkspace&, cudaStream_t, MsmResultShape*, unsigned*);
 INST(FpParams, FqParams)  // Pallas: coordinates Fp, scalars Fq
 INST(FqParams, FpParams)  // Vesta:  coordinates Fq, scalars Fp
 #undef INST

@@ -14,11 +14,16 @@
 //   * scalars are recoded to signed base-2^c digits in (-2^(c-1), 2^(c-1)]; (digit != 0) entries are counting-sorted by
 //     bucket (histogram -> scan -> scatter, all on device);
 //   * accumulation is task based: the histogram is known before any point is touched, so every bucket's sorted entries
-//     are cut into ceil(n_b / K) nearly equal tasks; a thread sums one task (<= K XYZZ mixed additions), a small lane
-//     group per bucket sums the task partials with a shuffle tree, and the rare giant bucket (all points in one
-//     bucket — the kimchi witness columns) gets a whole CTA.  No atomics touch curve points;
-//   * bucket reduction sum_b (b+1) B_b is evaluated bit-sliced: T_t = sum of the buckets whose (b+1) has bit t set —
-//     c masked tree sums, fully parallel — and the host finishes with c doublings.
+//     are cut into ceil(n_b / K) nearly equal tasks; a thread sums one task (<= K XYZZ mixed additions) and leaves one
+//     partial sum per task, in bucket order.  No atomics touch curve points;
+//   * bucket reduction sum_b (b+1) B_b never materialises the buckets: with b+1 = hi * W + lo the sum is
+//     W * sum_hi hi R[hi] + sum_lo lo C[lo], and the row sums R[hi] / column sums C[lo] are sums over TASK PARTIALS (a row is a
+//     contiguous range of the partial list), so one kernel goes from partials to the ~2 sqrt(B) row/column sums; a second one
+//     bit-slices those (T_t = sum of the rows / columns whose index has bit t set) and the host finishes with c doublings.
+//     The rare giant bucket (all points in one bucket: the kimchi witness columns) keeps its partials in a side
+//     area that 16 CTAs reduce to one slot first;
+//   * k MSMs over the same bases (the chunks of t, the 15 witness columns, the L/R pair of an IPA round) run as ONE pipeline
+//     with k bucket groups: every latency-bound stage is paid once per batch, not once per MSM.
 #pragma once
 #include <vector>
 
@@ -27,7 +32,11 @@
 namespace zkb {
 
 constexpr unsigned MSM_MAX_WINDOW_BITS = 16;
-constexpr uint32_t MSM_MAX_GIANTS = 64;       // buckets with > smax tasks get a CTA each (k_giant_finish)
+constexpr uint32_t MSM_MAX_GIANTS = 256;      // buckets with > smax tasks keep their partials in a side area (k_giant_finish)
+constexpr unsigned MSM_MAX_BATCH = 16;        // MSMs fused into one pipeline (scalar pointers travel as a kernel parameter)
+struct MsmScalarSet {
+    const fe* p[MSM_MAX_BATCH];
+};
 
 // A resident set of bases on one device.
 struct MsmBases {
@@ -41,27 +50,27 @@ struct MsmBases {
 // Growable device scratch of one context/device (sized for the largest call seen so far).
 struct MsmWorkspace {
     size_t cap_entries = 0, cap_partials = 0, cap_buckets = 0, cap_bits = 0, cap_hbits = 0;
-    int32_t* d_digits = nullptr;      // [nwin][n]
+    int32_t* d_digits = nullptr;      // [k][nwin][n]
     uint32_t* d_entries = nullptr;    // [M]  point index | sign << 31, sorted by bucket
-    xyzz_t* d_partials = nullptr;     // [tasks] one partial sum per accumulation task
-    uint32_t* d_counts = nullptr;     // [G*B]     histogram, then scatter cursors
-    uint32_t* d_offsets = nullptr;    // [G*B + 1] exclusive scan of the counts
-    uint32_t* d_task_off = nullptr;   // [G*B + 1] exclusive scan of ceil(count / K)
-    xyzz_t* d_buckets = nullptr;      // [G*B]
-    xyzz_t* d_bitsums = nullptr;      // [G][c][blocks] then [G][c]
+    xyzz_t* d_partials = nullptr;     // [tasks + giants] one partial sum per accumulation task (main slots, then giant areas)
+    uint32_t* d_counts = nullptr;     // [NB]     histogram, then scatter cursors
+    uint32_t* d_offsets = nullptr;    // [NB + 1] exclusive scan of the counts
+    uint32_t* d_task_off = nullptr;   // [NB + 1] exclusive scan of ceil(count / K)
+    uint64_t* d_chain = nullptr;      // [tiles] chained scan of k_plan: inclusive (entries << 32 | tasks) per tile
+    uint32_t* d_chain_flag = nullptr; // [tiles] epoch stamps of d_chain
+    uint32_t epoch = 0;               // bumped per run (no flag memset)
+    xyzz_t* d_bitsums = nullptr;      // row/column sums [G][nrows + W], then the slice sums [G][c]
     xyzz_t* h_bitsums = nullptr;      // pinned host copies of [G][c]: two slots (a lane may run ahead of the host tail by one MSM)
-    unsigned h_slot = 0;              // slot the next msm_run writes (result at h_bitsums + h_slot * G * c)
+    unsigned h_slot = 0;              // slot the next msm_run writes (result at h_bitsums + h_slot * cap_hbits)
     xyzz_t* d_T_out = nullptr;        // when set: the slice sums are copied HERE (device, capacity d_T_cap points) instead of to
     size_t d_T_cap = 0;               // the host, and nothing is synchronised (multi-GPU exchange, zk_msm_partial)
     bool defer_sync = false;          // msm_run returns after enqueueing the D2H copy; the caller synchronises
-    uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets
-    uint32_t* d_giants = nullptr;     // [MSM_MAX_GIANTS] bucket ids
+    uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets, [3] main slots, [4] plan tiles done
+    uint32_t* d_giants = nullptr;     // [3][MSM_MAX_GIANTS]: bucket ids | task counts | first slot of the side area
     xyzz_t* d_giant_slices = nullptr; // [MSM_MAX_GIANTS][GIANT_SLICES] per-CTA slice sums of a giant's partials
     uint32_t* d_giant_tickets = nullptr;  // [MSM_MAX_GIANTS] arrival counters (self-resetting)
-    int reduce_mode = 1;              // bucket reduction: 0 = bit-sliced sums over all buckets, 1 = two-level row/column sums
-    int finish_mode = 0;              // per-bucket sums of task partials: 0 = by shape, 1 = a thread per bucket, 2 = quads per bucket
-    uint32_t run_len = 4;             // k_run_sum: consecutive partials summed per thread before the per-bucket pass (0: off)
-    uint32_t chunk = 0;               // K override (0: chosen per call so that the tasks fill whole waves)
+    uint32_t chunk = 0;               // K override (0: chosen per call so that the tasks fill the machine once)
+    uint32_t wave_threads = 0;        // accumulation threads per SM the task count is sized for (0: built-in default)
     int sm_count = 148;               // SMs of the device (set by the context)
     bool profile = false;             // record an event after every stage
     cudaEvent_t ev[8] = {};           // MSM_ST_COUNT + 1 stage boundaries
@@ -79,19 +88,21 @@ void msm_bases_free(MsmBases& b);
 // Optional per-stage device timing (CUDA events on the launching stream), filled when MsmWorkspace::profile is set.
 enum MsmStage { MSM_ST_RECODE = 0, MSM_ST_PLAN, MSM_ST_SCATTER, MSM_ST_ACCUMULATE, MSM_ST_FINISH, MSM_ST_BITSUM, MSM_ST_COUNT };
 
-// What msm_run leaves in ws.h_bitsums: groups x c XYZZ points T[g][t]; the MSM is sum_g 2^(c g) sum_t 2^t T[g][t].
+// What msm_run leaves in ws.h_bitsums: batch x groups x c XYZZ points T[j][g][t]; MSM j is sum_g 2^(c g) sum_t 2^t T[j][g][t].
 struct MsmResultShape {
     unsigned c = 0, groups = 0;   // groups == 0: empty MSM (identity)
+    unsigned batch = 0;
 };
 
-// One MSM over bases[off .. off+n).  d_scalars_in: n scalars already on the device (8 u32 each).  window c: 0 = default
-// (ignored when the bases carry a precomputed table).  Synchronises the stream; the O(c) tail is finished by the caller.
+// k <= MSM_MAX_BATCH MSMs over bases[off .. off+n) in one pipeline.  d_scalars[j]: the n scalars of MSM j, already on the device
+// (8 u32 each).  window c: 0 = default (ignored when the bases carry a precomputed table).  Synchronises the stream (unless
+// ws.defer_sync / ws.d_T_out); the O(c) tail is finished by the caller.
 // out[i] = sum over r < world of all[r * count + i]   (the cross-rank sum of gathered slice sums, i < count)
 template <class F> int msm_sum_partials(const xyzz_t* d_all, size_t world, size_t count, xyzz_t* d_out, cudaStream_t st);
 
 template <class F, class FS>
-int msm_run(const MsmBases& b, size_t off, size_t n, const fe* d_scalars_in, bool scalars_mont, unsigned c, MsmWorkspace& ws,
-            cudaStream_t st, MsmResultShape* shape, unsigned* launches);
+int msm_run(const MsmBases& b, size_t off, size_t n, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
+            MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches);
 
 // group_ntt.cu: Lagrange-basis commitments of the domain of size 2^log_n from the resident generators (SRS::lagrange_basis)
 template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigned log_n, affine_t* d_out, cudaStream_t st, unsigned* launches);

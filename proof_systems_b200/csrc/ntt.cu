@@ -164,11 +164,9 @@ template <class F> __global__ void k_coset_scale(fe* data, size_t n, size_t len,
 template <class F> static int launch_pass(const NttPassParams& p, size_t batch_y, cudaStream_t st) {
     const unsigned S = 1u << p.log_s, T = 1u << p.log_t;
     size_t smem = (size_t)8 * T * (S + 1) * sizeof(uint32_t);
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        ZK_CUDA(cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    // the attribute is per (function, device): set it on every launch (a host-side table write) instead of caching a
+    // per-process flag that a second context on another device would never see
+    ZK_CUDA(cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid((unsigned)((p.ncols + T - 1) / T), (unsigned)batch_y);
     k_ntt_pass<F><<<grid, NTT_THREADS, smem, st>>>(p);
     ZK_CUDA(cudaGetLastError());

@@ -123,12 +123,12 @@ int zk_srs_get_lagrange_basis(zk_srs* srs, size_t domain_size, uint64_t* out_xy,
 // SRS::commit_non_hiding (ipa.rs:638-683)
 int zk_srs_commit_non_hiding(zk_srs* srs, const uint64_t* coeffs_mont, size_t len, size_t num_chunks, uint64_t* out_xy, size_t out_capacity, size_t* out_chunks) {
     if (!srs || !out_xy || !out_chunks || (!coeffs_mont && len)) { zk_set_error("commit_non_hiding: null argument"); return ZK_ERR_INVALID; }
-    // DensePolynomial invariant: trailing zero coefficients are not part of the polynomial; is_zero() == no coefficients
-    while (len > 0) {
-        const uint64_t* c = coeffs_mont + 4 * (len - 1);
-        if (c[0] | c[1] | c[2] | c[3]) break;
-        len--;
-    }
+    // plnm.is_zero() (ark-poly: no coefficients, or all of them zero) -> vec![G::zero()]; otherwise the chunk count comes from
+    // plnm.len() AS GIVEN (ipa.rs:646-676 never trims: an untrimmed coefficient vector with a zero tail still yields
+    // ceil(len / |g|) chunks, the last ones the identity)
+    bool all_zero = true;
+    for (size_t i = 0; i < 4 * len && all_zero; i++) all_zero = coeffs_mont[i] == 0;
+    if (all_zero) len = 0;
     const size_t n = srs->n;
     size_t produced = len == 0 ? 1 : (len + n - 1) / n;       // is_zero -> vec![G::zero()]
     size_t total = produced > num_chunks ? produced : num_chunks;  // pad with G::zero() up to num_chunks (ipa.rs:678-680)

@@ -26,6 +26,37 @@ def test_forward_and_inverse_match_oracle(ctx, orc, fid, log_n):
 
 
 @pytest.mark.parametrize("fid", [0, 1])
+@pytest.mark.parametrize("log_n", [17, 18, 19])
+def test_prover_domain_sizes_match_oracle(ctx, orc, fid, log_n):
+    """The d2 / d4 / d8 transforms of a 2^16-gate proof (kimchi/src/circuits/domains.rs:40-69): forward and inverse at full length,
+    the forward transform of n = 2^16 coefficients zero-padded to the larger domain (evaluate_over_domain_by_ref(d8),
+    kimchi/src/circuits/constraints.rs:488-507), and the inverse that follows the quotient (prover.rs:907), vs the oracle."""
+    n = 1 << log_n
+    a = orc.to_mont(fid, orc.random_scalars(fid, n, seed=60 + log_n))
+    assert np.array_equal(ctx.ntt(fid, a), orc.ntt(fid, a))
+    assert np.array_equal(ctx.ntt(fid, a, inverse=True), orc.ntt(fid, a, inverse=True))
+    padded = a.copy()
+    padded[1 << 16:] = 0
+    assert np.array_equal(ctx.ntt(fid, a, in_len=1 << 16), orc.ntt(fid, padded))
+
+
+@pytest.mark.parametrize("log_n", [17, 19])
+def test_batch_16_zero_padded_prover_shape(ctx, orc, log_n):
+    """constraints.rs:488-507: 15 witness columns + z, each n = 2^16 coefficients, evaluated over d2 / d8 in ONE batch call;
+    every polynomial of the batch must equal its own oracle transform (sampled columns at d8 to bound the CPU time)."""
+    fid, n, m, batch = zk.FP, 1 << log_n, 1 << 16, 16
+    a = np.zeros((batch, n, 4), dtype=np.uint64)
+    a[:, :m] = orc.to_mont(fid, orc.random_scalars(fid, batch * m, seed=71)).reshape(batch, m, 4)
+    garbage = a.copy()
+    garbage[:, m:] = orc.to_mont(fid, orc.random_scalars(fid, n - m, seed=72))      # beyond in_len: must be ignored
+    got = ctx.ntt(fid, garbage, in_len=m)
+    for j in (range(batch) if log_n == 17 else (0, 7, 15)):
+        assert np.array_equal(got[j], orc.ntt(fid, a[j])), j
+    back = ctx.ntt(fid, got, inverse=True)
+    assert np.array_equal(back, a)
+
+
+@pytest.mark.parametrize("fid", [0, 1])
 @pytest.mark.parametrize("log_n", [4, 10, 14])
 def test_coset_transforms_match_oracle(ctx, orc, fid, log_n):
     n = 1 << log_n

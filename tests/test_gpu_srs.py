@@ -51,6 +51,14 @@ def test_commit_non_hiding_expected_number_of_chunks(ctx, orc, request, name):
         for j in range(3):
             blk = orc.from_mont(g.scalar, p2[j * n:(j + 1) * n])
             assert np.array_equal(c2.chunks[j], orc.msm(g.cid, g.g[:len(blk)], blk)), j
+        # an UNTRIMMED coefficient vector (zero tail chunk): the chunk count follows plnm.len() as given (ipa.rs:646-676),
+        # the tail chunk is the identity; an all-zero vector is is_zero() -> one identity chunk
+        p3 = rand_poly(3 * n)
+        p3[2 * n:] = 0
+        c3 = srs.commit_non_hiding(p3, 1)
+        assert len(c3) == 3 and not np.any(c3.chunks[2]) and np.array_equal(c3.chunks[:2], srs.commit_non_hiding(p3[:2 * n], 1).chunks)
+        z3 = srs.commit_non_hiding(np.zeros((3 * n, 4), dtype=np.uint64), 1)
+        assert len(z3) == 1 and not np.any(z3.chunks)
         srs.close()
 
 
@@ -119,6 +127,16 @@ def test_device_point_decompression(ctx, orc, request, name):
     assert bad is not None
     with pytest.raises(zk.ZkError):
         ctx.decompress_points(g.cid, bad)
+    # non-canonical encodings are rejected like ark-serialize does (SWFlags::from_u8 + the field's canonical check): x = p,
+    # x = p + 1 (both reduce to valid small x values: 0 is off-curve, but p + 1 == 1 is the generator's x), stray low flag
+    # bits, and infinity together with the sign bit
+    p_int = orc.FP_MODULUS if g.base == orc.FP else orc.FQ_MODULUS
+    good = g.g_cmp[0].tobytes()
+    cases = [p_int.to_bytes(32, "little") + bytes([0]), (p_int + 1).to_bytes(32, "little") + bytes([0]),
+             good[:32] + bytes([good[32] | 0x01]), good[:32] + bytes([good[32] | 0x20]), bytes(32) + bytes([0xc0])]
+    for enc in cases:
+        with pytest.raises(zk.ZkError):
+            ctx.decompress_points(g.cid, good + enc)
 
 
 @pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
@@ -169,7 +187,8 @@ def test_srs_from_file(ctx, orc, vesta_srs, tmp_path):
 
 
 def test_commit_evaluations_batch_and_lanes(ctx, orc, pallas_srs):
-    """15 witness-like columns in one call (kimchi/src/prover.rs:329-351): identical to 15 single calls, for every lane count."""
+    """15 witness-like columns in one call (kimchi/src/prover.rs:329-351): identical to 15 single calls, whatever number of MSMs
+    is fused into one pipeline (16 = all of them, 1 = one pipeline per MSM, 4 = ragged groups)."""
     G = pallas_srs
     n = 2048
     srs = zk.SRS(ctx, G.cid, G.g[:n], G.mont_points(G.h_xy_canon)[0])
@@ -179,21 +198,21 @@ def test_commit_evaluations_batch_and_lanes(ctx, orc, pallas_srs):
     ev[4, : n - 5] = orc.to_mont(G.scalar, orc.ints_to_limbs([1]))[0]
     want = [orc.msm_mont(G.cid, G.mont_points(G.lag_2048_canon), ev[j]) for j in range(15)]
     try:
-        for lanes in (4, 1, 3):
-            ctx.set_option("msm_lanes", lanes)
+        for lanes in (16, 1, 4):
+            ctx.set_option("msm_batch", lanes)
             got = srs.commit_evaluations_non_hiding_batch(n, ev)
             for j in range(15):
                 assert np.array_equal(got[j].chunks[0], want[j]), (lanes, j)
         single = srs.commit_evaluations_non_hiding(n, ev[7])
         assert np.array_equal(single.chunks[0], want[7])
-        # chunked commit_non_hiding (7 chunks of t) goes through the same lanes
+        # chunked commit_non_hiding (7 chunks of t) goes through the same fused pipeline
         c7 = srs.commit_non_hiding(ev[:7].reshape(-1, 4), 7)
         for j in range(7):
             assert np.array_equal(c7.chunks[j], orc.msm_mont(G.cid, G.g[:n], ev[j]))
         with pytest.raises(zk.ZkError):
-            ctx.set_option("msm_lanes", 9)
+            ctx.set_option("msm_batch", 17)
     finally:
-        ctx.set_option("msm_lanes", 4)
+        ctx.set_option("msm_batch", 16)
     srs.close()
 
 

@@ -8,10 +8,9 @@ sys.path.insert(0, ROOT)
 import proof_systems_b200 as zk
 from bench import splitmix64_limbs
 ctx = zk.Context(0)
-if os.environ.get("MSM_REDUCE"): ctx.set_option("msm_reduce", int(os.environ["MSM_REDUCE"]))
 if os.environ.get("MSM_CHUNK"): ctx.set_option("msm_chunk", int(os.environ["MSM_CHUNK"]))
-if os.environ.get("MSM_FINISH"): ctx.set_option("msm_finish", int(os.environ["MSM_FINISH"]))
-if os.environ.get("MSM_RUN"): ctx.set_option("msm_run_len", int(os.environ["MSM_RUN"]))
+if os.environ.get("MSM_WAVE"): ctx.set_option("msm_wave_threads", int(os.environ["MSM_WAVE"]))
+WINDOW = int(os.environ.get("MSM_WINDOW", "-1"))
 KS = [int(x) for x in os.environ.get("MSM_LOGS", "8,10,11,12,13,14,15,16").split(",")]
 stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -27,7 +26,7 @@ def timed(fn, reps=7):
 rows = []
 for k in KS:
     n = 1 << k
-    bases = ctx.upload_bases(zk.PALLAS, g[:n])
+    bases = ctx.upload_bases(zk.PALLAS, g[:n], window_bits=WINDOW)
     for kind in ("uniform", "ones"):
         sc = splitmix64_limbs(k, n)
         if kind == "ones":
@@ -38,4 +37,4 @@ for k in KS:
         rows.append({"log_n": k, "scalars": kind, "window": bases.window_bits, "ms": round(t, 4), "stages_us": {a: round(1e3 * b, 1) for a, b in st.items()}})
         print(rows[-1], flush=True)
     bases.free()
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "msm_sizes.json"), "w"), indent=1)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", os.environ.get("MSM_OUT", "msm_sizes.json")), "w"), indent=1)
