@@ -187,6 +187,46 @@ int zk_ipa_round_lr(zk_ipa* ipa, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12],
 int zk_ipa_round_fold(zk_ipa* ipa, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]);
 int zk_ipa_read(zk_ipa* ipa, uint64_t* out_a, uint64_t* out_b, size_t capacity, uint64_t out_g_xyz[12]);
 
+/* ------------------------------------------------------------------ SRS::open as one call (poly-commitment/src/ipa.rs:823-1061)
+ * == <OpeningProof<G> as OpenProof<G>>::open(srs, group_map, plnms, elm, polyscale, evalscale, sponge, rng)  (ipa.rs:1193-1218).
+ * Everything with arithmetic in it runs in the library: combine_polys (utils.rs:103-202: scaled accumulation of the batch, the
+ * iFFT of the evaluation-form part, chunk linearisation), b_init (ipa.rs:876-888), the combined inner product (:891-896), the
+ * log2 |g| folding rounds (:929-1007; h and U ride as two extra bases of every round's MSM pair exactly like the reference's
+ * `[g_lo, &[self.h, u_base]].concat()`), r_prime, delta, z1, z2 (:1022-1052).  What stays with the caller is what the reference
+ * keeps generic: the Fiat-Shamir sponge and the group map behind three callbacks, and the random scalars, passed in the order
+ * the reference draws them (rand_l, rand_r per round, then d, r_delta).
+ *
+ * zk_open_poly: one entry of `plnms` — DensePolynomialOrEvaluations + the PolyComm of blinders (utils.rs:18-23, 84-94).
+ *   data         Montgomery field elements: coefficients, or evaluations; host (pageable or page-locked) or DEVICE memory
+ *   len          element count
+ *   domain_size  0 = DensePolynomial; otherwise Evaluations over the domain of that size, len a multiple of it (stride = len /
+ *                domain_size, utils.rs:151-158); every evaluation-form entry must use the same domain (the reference asserts)
+ *   blinders     the chunks of the blinder commitment `p_i_comm` (Montgomery scalars), n_blinders of them
+ * Callbacks return 0 on success; any other value aborts the call with ZK_ERR_INVALID. */
+typedef struct zk_open_poly {
+    const uint64_t* data;
+    size_t len;
+    size_t domain_size;
+    const uint64_t* blinders;
+    size_t n_blinders;
+} zk_open_poly;
+typedef struct zk_open_transcript {
+    void* user;
+    /* ipa.rs:898-910: sponge.absorb_fr(shift_scalar(combined_inner_product)); t = sponge.challenge_fq();
+     * U = group_map.to_group(t).  in: combined_inner_product (Montgomery scalar); out: U, affine Montgomery */
+    int (*u_base)(void* user, const uint64_t combined_inner_product[4], uint64_t out_u_xy[8]);
+    /* ipa.rs:962-970: absorb_g(l), absorb_g(r); u = squeeze_prechallenge(sponge).to_field(endo_r).  out: u (Montgomery scalar) */
+    int (*round)(void* user, unsigned round, const uint64_t l_xy[8], const uint64_t r_xy[8], uint64_t out_u[4]);
+    /* ipa.rs:1040-1041: absorb_g(delta); c = ScalarChallenge(sponge.challenge()).to_field(endo_r).  out: c (Montgomery scalar) */
+    int (*final_challenge)(void* user, const uint64_t delta_xy[8], uint64_t out_c[4]);
+} zk_open_transcript;
+/* rounds = ceil(log2 |g|).  rng_scalars: 2 * rounds + 2 Montgomery scalars (n_rng_scalars must say so).
+ * out_lr_xy: rounds x 2 affine points (l_0, r_0, l_1, ...), capacity lr_capacity_rounds rounds; out_rounds receives rounds. */
+int zk_srs_open(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, const uint64_t* elm_mont, size_t n_elm,
+                const uint64_t polyscale[4], const uint64_t evalscale[4], const uint64_t* rng_scalars, size_t n_rng_scalars,
+                const zk_open_transcript* transcript, uint64_t* out_lr_xy, size_t lr_capacity_rounds, size_t* out_rounds,
+                uint64_t out_delta_xy[8], uint64_t out_z1[4], uint64_t out_z2[4], uint64_t out_sg_xy[8]);
+
 /* ------------------------------------------------------------------ diagnostics (tests/test_gpu_field.py, DESIGN.md compute model)
  * Element-wise device field ops on n elements (op: 0 mul, 1 add, 2 sub, 3 inverse of a), host pointers. */
 int zk_debug_field_op(zk_ctx* ctx, int field_id, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

@@ -97,7 +97,26 @@ def lib() -> ctypes.CDLL:
     L.zk_debug_mul_throughput.argtypes = [vp, i, u, ctypes.POINTER(ctypes.c_double)]
     L.zk_debug_op_throughput.argtypes = [vp, i, i, u, u, u, ctypes.POINTER(ctypes.c_double)]
     _lib = L
+    L.zk_srs_open.argtypes = [vp, ctypes.POINTER(OpenPoly), sz, vp, sz, vp, vp, vp, sz, ctypes.POINTER(OpenTranscript), vp, sz,
+                              ctypes.POINTER(sz), vp, vp, vp, vp]
     return L
+
+
+class OpenPoly(ctypes.Structure):
+    """zk_open_poly (include/zkb200.h)"""
+    _fields_ = [("data", ctypes.c_void_p), ("len", ctypes.c_size_t), ("domain_size", ctypes.c_size_t),
+                ("blinders", ctypes.c_void_p), ("n_blinders", ctypes.c_size_t)]
+
+
+U_BASE_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64))
+ROUND_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                            ctypes.POINTER(ctypes.c_uint64))
+FINAL_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64))
+
+
+class OpenTranscript(ctypes.Structure):
+    """zk_open_transcript (include/zkb200.h)"""
+    _fields_ = [("user", ctypes.c_void_p), ("u_base", U_BASE_CB), ("round", ROUND_CB), ("final_challenge", FINAL_CB)]
 
 
 def check(rc: int):

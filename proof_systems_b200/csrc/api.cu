@@ -51,12 +51,12 @@ static void xyzz_to_jac_out(int curve, const host::hxyzz& p, uint64_t out[12]) {
 }
 
 int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
-                 uint64_t* out_xyz) {
+                 uint64_t* out_xyz, const affine_t* d_extra, size_t n_extra) {
     if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
     const bool pallas = bases->b.curve == ZK_PALLAS;
     // MSMs per pipeline: the context's limit, and no more than keeps the sorted entry list below 2^28 entries (1 GiB of scratch)
     const unsigned c_eff = bases->b.c ? bases->b.c : (window_bits ? (unsigned)window_bits : (unsigned)msm_default_window(n, false));
-    const size_t per_msm = std::max<size_t>(1, n * msm_num_windows(std::max(2u, c_eff)));
+    const size_t per_msm = std::max<size_t>(1, (n + n_extra) * msm_num_windows(std::max(2u, c_eff)));
     size_t fuse = std::min<size_t>((size_t)std::max(1, ctx->batch), std::max<size_t>(1, ((size_t)1 << 28) / per_msm));
     if (ctx->profile) fuse = 1;   // stage times are those of ONE MSM (zk_ctx_last_stage_ms)
     for (size_t j0 = 0; j0 < k; j0 += fuse) {
@@ -64,8 +64,10 @@ int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const
         MsmResultShape shape;
         unsigned nl = 0;
         ctx->ws.h_slot = 0;
-        int rc = pallas ? msm_run<FpParams, FqParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl)
-                        : msm_run<FqParams, FpParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
+        int rc = pallas ? msm_run<FpParams, FqParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl,
+                                                      d_extra, n_extra)
+                        : msm_run<FqParams, FpParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl,
+                                                      d_extra, n_extra);
         if (rc) return rc;
         ctx->launches += nl;
         for (unsigned j = 0; j < cnt; j++) {
@@ -124,7 +126,7 @@ static int ctx_ntt_tables(zk_ctx* ctx, int field, unsigned log_n, bool inverse, 
     return ZK_OK;
 }
 
-static int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
+int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
     if (field != ZK_FP && field != ZK_FQ) { zk_set_error("ntt: unknown field_id %d", field); return ZK_ERR_INVALID; }
     if (log_n > NTT_MAX_LOG_N) { zk_set_error("ntt: log_n %u > %u not supported", log_n, NTT_MAX_LOG_N); return ZK_ERR_INVALID; }
     const fe* small;
@@ -257,6 +259,7 @@ void zk_ctx_destroy(zk_ctx* ctx) {
     if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
     if (ctx->d_gather_sum) cudaFree(ctx->d_gather_sum);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    if (ctx->d_open) cudaFree(ctx->d_open);
     if (ctx->d_ntt) cudaFree(ctx->d_ntt);
     if (ctx->d_ntt_tmp) cudaFree(ctx->d_ntt_tmp);
     for (int f = 0; f < 2; f++) for (int d = 0; d < 2; d++) if (ctx->ntt_small[f][d]) cudaFree(ctx->ntt_small[f][d]);

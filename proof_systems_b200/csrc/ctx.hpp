@@ -28,6 +28,8 @@ struct zk_ctx {
     zkb::xyzz_t* h_gather = nullptr;     // ... and their pinned host copy
     size_t cap_h_gather = 0;
     void* h_scratch = nullptr;           // 256 pinned bytes for small read-backs
+    void* d_open = nullptr;              // zk_srs_open: staged polynomials | evaluation part | descriptors | extra bases
+    size_t cap_open = 0;
     uint64_t launches = 0;
     bool profile = false;                // per-stage device timing (zk_ctx_set_profile)
     cudaEvent_t ev_ntt[2] = {nullptr, nullptr};
@@ -43,8 +45,21 @@ namespace zkb {
 int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* d_scalars, int mont, int window_bits,
                    uint64_t out_xyz[12]);
 int ctx_ensure(void** p, size_t* cap, size_t bytes);
+// the NTT of zk_ntt_dev without the context lock (the caller holds it)
+int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset);
 // k independent MSMs over the same bases slice [off, off + n), scalars j at d_scalars[j] (device memory, ordered after
 // ctx->stream), fused into pipelines of up to ctx->batch MSMs (msm.cuh).  Results (Jacobian) to out_xyz + 12 j.
+// d_extra / n_extra: points of this call only, laid out like the table (msm.cuh); every scalar vector then has n + n_extra entries.
 int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
-                 uint64_t* out_xyz);
+                 uint64_t* out_xyz, const affine_t* d_extra = nullptr, size_t n_extra = 0);
 }  // namespace zkb
+
+// host-side mirror of poly_commitment::ipa::SRS<G> (srs.cu); shared with the opening proof (open.cu)
+struct zk_srs {
+    zk_ctx* ctx = nullptr;
+    int curve = 0;
+    size_t n = 0;                       // |g| = max_poly_size
+    zk_bases* g = nullptr;              // resident generators
+    uint64_t h[8];                      // blinding base
+    std::map<size_t, zk_bases*> lagrange;  // domain size -> resident Lagrange basis (one chunk per element: domain <= |g|)
+};

@@ -7,37 +7,24 @@
 //     R_j = <a_lo, g_j,hi> = sum_{t, i < h} (a[i] s_j[t])     g[t m_j + h + i]
 // and the final base g0 (the proof's `sg`) is <s_k, g>.  That replaces log2(n) rounds of per-point scalar multiplications
 // (G::combine_one_endo, commitment.rs:539 / combine.rs:292-342 — latency-bound chains of ~380 group operations per point) by
-// the throughput-bound MSM pipeline of msm.cu; the group elements produced are the same.  The host owns the Fiat-Shamir
-// sponge, rand_l / rand_r, h and u_base: it finishes L and R (two scalar multiplications), squeezes u, and asks for the fold
+// the throughput-bound MSM pipeline of msm.cu; the group elements produced are the same.  L and R of a round are ONE fused
+// pipeline (two bucket groups).  Two ways to drive the rounds:
+//   zk_ipa_*      the bare rounds: the host owns the Fiat-Shamir sponge, rand_l / rand_r, h and u_base; it finishes L and R
+//                 (two scalar multiplications each), squeezes u, and asks for the fold
+//   zk_srs_open   (open.cu) the whole SRS::open: h and U are two extra points of the same MSMs, their scalars (the blinders and
+//                 the inner products) are appended on the device, so a round returns the finished L and R
 //     a <- a_lo + u^-1 a_hi,   b <- b_lo + u b_hi,   s <- (s[t], u s[t])_t          (ipa.rs:980-1006)
 // SURVEY.md §8f row 1.
 #include <mutex>
 
 #include "../../include/zkb200.h"
-#include "ctx.hpp"
 #include "host_field.hpp"
+#include "ipa.hpp"
 #include "msm.cuh"
 
 using namespace zkb;
 
-struct zk_ipa {
-    zk_ctx* ctx = nullptr;
-    int curve = 0;
-    size_t n = 0;           // current length (halves every fold)
-    size_t n0 = 0;          // original (padded) length
-    const zk_bases* bases = nullptr;
-    fe* d_s[2] = {nullptr, nullptr};   // b_poly_coefficients of the challenges so far (ping-pong), Montgomery
-    int cur = 0;
-    fe* d_sc = nullptr;     // expanded MSM scalars of L and of R, 2 x n0 entries, Montgomery
-    fe* d_a = nullptr;
-    fe* d_b = nullptr;
-    fe* d_part = nullptr;   // inner-product partials
-    fe* h_ip = nullptr;     // pinned (the context's scratch): two field elements
-};
-
 namespace zkb {
-
-constexpr unsigned IP_THREADS = 256, IP_BLOCKS = 64;
 
 // partial[blockIdx] = sum over the block's strided share of x[i] * y[i]  (Montgomery in, Montgomery out)
 template <class FS> __global__ void __launch_bounds__(IP_THREADS) k_inner_product(const fe* __restrict__ x, const fe* __restrict__ y, size_t m, fe* partial) {
@@ -90,61 +77,140 @@ template <class FS> __global__ void k_expand_scalars(fe* sc, const fe* __restric
     store_fe(sc + idx, v);
 }
 
-template <class FS> static int inner_product(zk_ipa* s, const fe* x, const fe* y, size_t m, fe* d_out) {
+// the scalars of the two extra points (h, U) behind the `len` base scalars of L and of R:  (rand_l, <a_hi, b_lo>), (rand_r, <a_lo, b_hi>)
+__global__ void k_tail_scalars(fe* sc_l, fe* sc_r, size_t len, const fe* __restrict__ rand_lr, const fe* __restrict__ ips) {
+    if (threadIdx.x == 0) { store_fe(sc_l + len, load_fe(rand_lr)); store_fe(sc_l + len + 1, load_fe(ips)); }
+    if (threadIdx.x == 1) { store_fe(sc_r + len, load_fe(rand_lr + 1)); store_fe(sc_r + len + 1, load_fe(ips + 1)); }
+}
+
+template <class FS> int ipa_inner_product(zk_ipa* s, const fe* x, const fe* y, size_t m, fe* d_out) {
     k_inner_product<FS><<<IP_BLOCKS, IP_THREADS, 0, s->ctx->stream>>>(x, y, m, s->d_part);
     k_inner_product_final<FS><<<1, IP_BLOCKS, 0, s->ctx->stream>>>(s->d_part, d_out);
     ZK_CUDA(cudaGetLastError());
     s->ctx->launches += 2;
     return ZK_OK;
 }
-
-}  // namespace zkb
+template int ipa_inner_product<FpParams>(zk_ipa*, const fe*, const fe*, size_t, fe*);
+template int ipa_inner_product<FqParams>(zk_ipa*, const fe*, const fe*, size_t, fe*);
 
 // L and R of one round: both scalar vectors are expanded on the main stream, the two MSMs run as ONE fused pipeline
 template <class FS> static int ipa_expand_and_msm(zk_ipa* s, size_t h, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12]) {
     zk_ctx* ctx = s->ctx;
     const unsigned blocks = (unsigned)((s->n0 + 255) / 256);
-    k_expand_scalars<FS><<<blocks, 256, 0, ctx->stream>>>(s->d_sc, s->d_a, s->d_s[s->cur], s->n0, h, 0);
-    k_expand_scalars<FS><<<blocks, 256, 0, ctx->stream>>>(s->d_sc + s->n0, s->d_a, s->d_s[s->cur], s->n0, h, 1);
-    ZK_CUDA(cudaGetLastError());
+    const size_t stride = s->n0 + 2;                                    // room for the two extra scalars
+    fe *sc_l = s->d_sc, *sc_r = s->d_sc + stride;
+    k_expand_scalars<FS><<<blocks, 256, 0, ctx->stream>>>(sc_l, s->d_a, s->d_s[s->cur], s->n0, h, 0);
+    k_expand_scalars<FS><<<blocks, 256, 0, ctx->stream>>>(sc_r, s->d_a, s->d_s[s->cur], s->n0, h, 1);
     ctx->launches += 2;
     const size_t len = s->n0 < s->bases->b.n ? s->n0 : s->bases->b.n;   // positions past the SRS are identity padding
-    const fe* scs[2] = {s->d_sc, s->d_sc + s->n0};
+    const bool extras = s->d_extra != nullptr;
+    if (extras) {
+        k_tail_scalars<<<1, 32, 0, ctx->stream>>>(sc_l, sc_r, len, s->d_rand + 2 * s->round, s->d_part + IP_BLOCKS);
+        ctx->launches += 1;
+    }
+    ZK_CUDA(cudaGetLastError());
+    const fe* scs[2] = {sc_l, sc_r};
     uint64_t out[24];
-    int rc = ctx_msm_many(ctx, s->bases, 0, len, scs, 2, /*mont=*/1, 0, out);
+    int rc = ctx_msm_many(ctx, s->bases, 0, len, scs, 2, /*mont=*/1, 0, out, s->d_extra, extras ? 2 : 0);
     if (rc) return rc;
     memcpy(out_l_xyz, out, 96);
     memcpy(out_r_xyz, out + 12, 96);
     return ZK_OK;
 }
 
-static void ipa_release(zk_ipa* s) {
+void ipa_release(zk_ipa* s) {
+    if (!s) return;
     cudaFree(s->d_a);
     delete s;
 }
+
+int ipa_create(zk_ctx* ctx, const zk_bases* bases, size_t n, zk_ipa** out) {
+    if (n < 1 || (n & (n - 1))) { zk_set_error("ipa: n must be a power of two (the reference pads to a power of two, ipa.rs:848-850)"); return ZK_ERR_INVALID; }
+    if (bases->b.n > n || (n > 1 && 2 * bases->b.n <= n)) { zk_set_error("ipa: n = %zu is not the SRS size %zu rounded up to a power of two", n, bases->b.n); return ZK_ERR_INVALID; }
+    zk_ipa* s = new zk_ipa();
+    s->ctx = ctx; s->curve = bases->b.curve; s->n = s->n0 = n; s->bases = bases;
+    const fe one = s->curve == ZK_PALLAS ? fe_one<FqParams>() : fe_one<FpParams>();
+    // one device allocation: a | b | s0 | s1 | sc_L (+2) | sc_R (+2) | partials (+ two inner products)
+    cudaError_t e = cudaMalloc(&s->d_a, (6 * n + 4 + IP_BLOCKS + 2) * sizeof(fe));
+    if (e == cudaSuccess) {
+        s->d_b = s->d_a + n; s->d_s[0] = s->d_a + 2 * n; s->d_s[1] = s->d_a + 3 * n; s->d_sc = s->d_a + 4 * n; s->d_part = s->d_a + 6 * n + 4;
+        if (!ctx->h_scratch) e = cudaMallocHost(&ctx->h_scratch, 256);
+        s->h_ip = (fe*)ctx->h_scratch;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_s[0], &one, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);   // s_0 = (1)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // `one` is a stack temporary
+    if (e != cudaSuccess) {
+        zk_set_error("ipa: %s", cudaGetErrorString(e));
+        ipa_release(s);
+        return ZK_ERR_CUDA;
+    }
+    *out = s;
+    return ZK_OK;
+}
+
+int ipa_round_lr(zk_ipa* s, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12], uint64_t out_ip_l[4], uint64_t out_ip_r[4]) {
+    if (s->n < 2) { zk_set_error("ipa_round_lr: folding is complete"); return ZK_ERR_INVALID; }
+    zk_ctx* ctx = s->ctx;
+    const size_t h = s->n / 2;
+    const bool pallas = s->curve == ZK_PALLAS;   // scalar field of Pallas is Fq
+    // inner products <a_hi, b_lo>, <a_lo, b_hi>
+    int rc = pallas ? ipa_inner_product<FqParams>(s, s->d_a + h, s->d_b, h, s->d_part + IP_BLOCKS)
+                    : ipa_inner_product<FpParams>(s, s->d_a + h, s->d_b, h, s->d_part + IP_BLOCKS);
+    if (rc) return rc;
+    rc = pallas ? ipa_inner_product<FqParams>(s, s->d_a, s->d_b + h, h, s->d_part + IP_BLOCKS + 1)
+                : ipa_inner_product<FpParams>(s, s->d_a, s->d_b + h, h, s->d_part + IP_BLOCKS + 1);
+    if (rc) return rc;
+    if (out_ip_l) ZK_CUDA(cudaMemcpyAsync(s->h_ip, s->d_part + IP_BLOCKS, 2 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = pallas ? ipa_expand_and_msm<FqParams>(s, h, out_l_xyz, out_r_xyz) : ipa_expand_and_msm<FpParams>(s, h, out_l_xyz, out_r_xyz);
+    if (rc) return rc;
+    if (out_ip_l) {
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(out_ip_l, &s->h_ip[0], 32);
+        memcpy(out_ip_r, &s->h_ip[1], 32);
+    }
+    return ZK_OK;
+}
+
+int ipa_round_fold(zk_ipa* s, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]) {
+    if (s->n < 2) { zk_set_error("ipa_round_fold: folding is complete"); return ZK_ERR_INVALID; }
+    zk_ctx* ctx = s->ctx;
+    const size_t h = s->n / 2, count = s->n0 / s->n;   // count = 2^j challenges products so far
+    fe u, ui;
+    memcpy(u.v, u_mont, 32);
+    memcpy(ui.v, u_inv_mont, 32);
+    const unsigned blocks = (unsigned)((h + 127) / 128), sblocks = (unsigned)((count + 127) / 128);
+    if (s->curve == ZK_PALLAS) {
+        k_fold_field<FqParams><<<blocks, 128, 0, ctx->stream>>>(s->d_a, h, ui);
+        k_fold_field<FqParams><<<blocks, 128, 0, ctx->stream>>>(s->d_b, h, u);
+        k_expand_challenges<FqParams><<<sblocks, 128, 0, ctx->stream>>>(s->d_s[s->cur], s->d_s[s->cur ^ 1], count, u);
+    } else {
+        k_fold_field<FpParams><<<blocks, 128, 0, ctx->stream>>>(s->d_a, h, ui);
+        k_fold_field<FpParams><<<blocks, 128, 0, ctx->stream>>>(s->d_b, h, u);
+        k_expand_challenges<FpParams><<<sblocks, 128, 0, ctx->stream>>>(s->d_s[s->cur], s->d_s[s->cur ^ 1], count, u);
+    }
+    ZK_CUDA(cudaGetLastError());
+    ctx->launches += 3;
+    s->cur ^= 1;
+    s->n = h;
+    s->round += 1;
+    return ZK_OK;
+}
+
+}  // namespace zkb
 
 extern "C" {
 
 int zk_ipa_begin(zk_ctx* ctx, const zk_bases* bases, const uint64_t* a_mont, const uint64_t* b_mont, size_t n, zk_ipa** out) {
     if (!ctx || !bases || !a_mont || !b_mont || !out) { zk_set_error("ipa_begin: null argument"); return ZK_ERR_INVALID; }
     if (bases->ctx != ctx) { zk_set_error("ipa_begin: bases belong to another context"); return ZK_ERR_INVALID; }
-    if (n < 2 || (n & (n - 1))) { zk_set_error("ipa_begin: n must be a power of two >= 2 (the reference pads to a power of two, ipa.rs:848-850)"); return ZK_ERR_INVALID; }
-    if (bases->b.n > n || 2 * bases->b.n <= n) { zk_set_error("ipa_begin: n = %zu is not the SRS size %zu rounded up to a power of two", n, bases->b.n); return ZK_ERR_INVALID; }
+    if (n < 2) { zk_set_error("ipa_begin: n must be a power of two >= 2 (the reference pads to a power of two, ipa.rs:848-850)"); return ZK_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));
-    zk_ipa* s = new zk_ipa();
-    s->ctx = ctx; s->curve = bases->b.curve; s->n = s->n0 = n; s->bases = bases;
-    const fe one = s->curve == ZK_PALLAS ? fe_one<FqParams>() : fe_one<FpParams>();
-    // one device allocation: a | b | s0 | s1 | sc_L | sc_R | partials
-    cudaError_t e = cudaMalloc(&s->d_a, (6 * n + IP_BLOCKS + 2) * sizeof(fe));
-    if (e == cudaSuccess) {
-        s->d_b = s->d_a + n; s->d_s[0] = s->d_a + 2 * n; s->d_s[1] = s->d_a + 3 * n; s->d_sc = s->d_a + 4 * n; s->d_part = s->d_a + 6 * n;
-        if (!ctx->h_scratch) e = cudaMallocHost(&ctx->h_scratch, 256);
-        s->h_ip = (fe*)ctx->h_scratch;
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_a, a_mont, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
+    zk_ipa* s = nullptr;
+    int rc = ipa_create(ctx, bases, n, &s);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(s->d_a, a_mont, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_b, b_mont, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_s[0], &one, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);   // s_0 = (1)
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         zk_set_error("ipa_begin: %s", cudaGetErrorString(e));
@@ -166,53 +232,16 @@ size_t zk_ipa_len(const zk_ipa* s) { return s ? s->n : 0; }
 
 int zk_ipa_round_lr(zk_ipa* s, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12], uint64_t out_ip_l[4], uint64_t out_ip_r[4]) {
     if (!s || !out_l_xyz || !out_r_xyz || !out_ip_l || !out_ip_r) { zk_set_error("ipa_round_lr: null argument"); return ZK_ERR_INVALID; }
-    if (s->n < 2) { zk_set_error("ipa_round_lr: folding is complete"); return ZK_ERR_INVALID; }
-    zk_ctx* ctx = s->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ZK_CUDA(cudaSetDevice(ctx->device));
-    const size_t h = s->n / 2;
-    const bool pallas = s->curve == ZK_PALLAS;   // scalar field of Pallas is Fq
-    // inner products <a_hi, b_lo>, <a_lo, b_hi>
-    int rc = pallas ? inner_product<FqParams>(s, s->d_a + h, s->d_b, h, s->d_part + IP_BLOCKS)
-                    : inner_product<FpParams>(s, s->d_a + h, s->d_b, h, s->d_part + IP_BLOCKS);
-    if (rc) return rc;
-    rc = pallas ? inner_product<FqParams>(s, s->d_a, s->d_b + h, h, s->d_part + IP_BLOCKS + 1)
-                : inner_product<FpParams>(s, s->d_a, s->d_b + h, h, s->d_part + IP_BLOCKS + 1);
-    if (rc) return rc;
-    ZK_CUDA(cudaMemcpyAsync(s->h_ip, s->d_part + IP_BLOCKS, 2 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = pallas ? ipa_expand_and_msm<FqParams>(s, h, out_l_xyz, out_r_xyz) : ipa_expand_and_msm<FpParams>(s, h, out_l_xyz, out_r_xyz);
-    if (rc) return rc;
-    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(out_ip_l, &s->h_ip[0], 32);
-    memcpy(out_ip_r, &s->h_ip[1], 32);
-    return ZK_OK;
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    ZK_CUDA(cudaSetDevice(s->ctx->device));
+    return ipa_round_lr(s, out_l_xyz, out_r_xyz, out_ip_l, out_ip_r);
 }
 
 int zk_ipa_round_fold(zk_ipa* s, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]) {
     if (!s || !u_mont || !u_inv_mont) { zk_set_error("ipa_round_fold: null argument"); return ZK_ERR_INVALID; }
-    if (s->n < 2) { zk_set_error("ipa_round_fold: folding is complete"); return ZK_ERR_INVALID; }
-    zk_ctx* ctx = s->ctx;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ZK_CUDA(cudaSetDevice(ctx->device));
-    const size_t h = s->n / 2, count = s->n0 / s->n;   // count = 2^j challenges products so far
-    fe u, ui;
-    memcpy(u.v, u_mont, 32);
-    memcpy(ui.v, u_inv_mont, 32);
-    const unsigned blocks = (unsigned)((h + 127) / 128), sblocks = (unsigned)((count + 127) / 128);
-    if (s->curve == ZK_PALLAS) {
-        k_fold_field<FqParams><<<blocks, 128, 0, ctx->stream>>>(s->d_a, h, ui);
-        k_fold_field<FqParams><<<blocks, 128, 0, ctx->stream>>>(s->d_b, h, u);
-        k_expand_challenges<FqParams><<<sblocks, 128, 0, ctx->stream>>>(s->d_s[s->cur], s->d_s[s->cur ^ 1], count, u);
-    } else {
-        k_fold_field<FpParams><<<blocks, 128, 0, ctx->stream>>>(s->d_a, h, ui);
-        k_fold_field<FpParams><<<blocks, 128, 0, ctx->stream>>>(s->d_b, h, u);
-        k_expand_challenges<FpParams><<<sblocks, 128, 0, ctx->stream>>>(s->d_s[s->cur], s->d_s[s->cur ^ 1], count, u);
-    }
-    ZK_CUDA(cudaGetLastError());
-    ctx->launches += 3;
-    s->cur ^= 1;
-    s->n = h;
-    return ZK_OK;
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    ZK_CUDA(cudaSetDevice(s->ctx->device));
+    return ipa_round_fold(s, u_mont, u_inv_mont);
 }
 
 // Current state: copies min(len, capacity) leading elements of a and b (Montgomery); out_g_xyz (optional) receives the first
@@ -228,7 +257,6 @@ int zk_ipa_read(zk_ipa* s, uint64_t* out_a, uint64_t* out_b, size_t capacity, ui
     if (out_a && m) ZK_CUDA(cudaMemcpy(out_a, s->d_a, m * sizeof(fe), cudaMemcpyDeviceToHost));
     if (out_b && m) ZK_CUDA(cudaMemcpy(out_b, s->d_b, m * sizeof(fe), cudaMemcpyDeviceToHost));
     if (out_g_xyz) {
-        // g_j[0] = sum_t s_j[t] g[t * m_j]: scalars a == (1, 0, 0, ...) per block — expand with a one-hot "a"
         if (s->n != 1) { zk_set_error("ipa_read: the folded base is available after the last round only"); return ZK_ERR_INVALID; }
         const size_t len = s->n0 < s->bases->b.n ? s->n0 : s->bases->b.n;
         return ctx_msm_device(ctx, s->bases, 0, len, s->d_s[s->cur], /*mont=*/1, 0, out_g_xyz);

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offse
 
 // Counting-sort scatter: entry (point index | sign) of every non-zero digit goes to its bucket's range.
 __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned nwin, unsigned batch, unsigned gpm, int per_window, size_t base_off,
-                          size_t table_stride, int use_table, const uint32_t* offsets, uint32_t* cursors, uint32_t* entries) {
+                          size_t table_stride, int use_table, size_t n_main, size_t n_extra, uint32_t main_count, const uint32_t* offsets,
+                          uint32_t* cursors, uint32_t* entries) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = id < n * nwin * batch;
     int32_t sd = in_range ? digits[id] : 0;
@@ -209,7 +210,9 @@ __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned 
     base = __shfl_sync(0xffffffffu, base, leader);
     if (sd == 0) return;
     uint32_t pos = offsets[key] + base + (uint32_t)__popc(peers & ((1u << lane) - 1));
-    size_t pidx = (use_table ? (size_t)w * table_stride : 0) + base_off + i;
+    // scalars [0, n_main) belong to the resident bases, [n_main, n) to the call's extra points (their rows behind the table)
+    size_t pidx = i < n_main ? (use_table ? (size_t)w * table_stride : 0) + base_off + i
+                             : (size_t)main_count + (use_table ? (size_t)w * n_extra : 0) + (i - n_main);
     entries[pos] = (uint32_t)pidx | (sd < 0 ? 0x80000000u : 0u);
 }
 
@@ -244,7 +247,7 @@ template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__ points, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
                                                     uint32_t K, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ giants,
-                                                    xyzz_t* partials) {
+                                                    const affine_t* __restrict__ extra, uint32_t main_count, xyzz_t* partials) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= __ldg(meta + 1)) return;
     // upper_bound(task_off[0..nb], t) - 1
@@ -261,14 +264,17 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
     const uint32_t end = i + base + (sub < rem ? 1u : 0u);
     xyzz_t acc = xyzz_identity();
     // software pipeline: the gather of point i+1 is in flight while point i is added
+    // (entries >= main_count address the call's extra points: h and U of an IPA round, ipa.rs:944,954)
     uint32_t e = __ldg(entries + i);
-    affine_t p = load_affine_nc(points + (e & 0x7fffffffu));
+    uint32_t idx = e & 0x7fffffffu;
+    affine_t p = load_affine_nc(idx < main_count ? points + idx : extra + (idx - main_count));
     for (; i < end; i++) {
         affine_t q = p;
         const uint32_t sign = e >> 31;
         if (i + 1 < end) {
             e = __ldg(entries + i + 1);
-            p = load_affine_nc(points + (e & 0x7fffffffu));
+            idx = e & 0x7fffffffu;
+            p = load_affine_nc(idx < main_count ? points + idx : extra + (idx - main_count));
         }
         if (sign) q.y = fe_neg<F>(q.y);
         acc = xyzz_madd<F>(acc, q);
@@ -486,9 +492,11 @@ void msm_workspace_free(MsmWorkspace& ws) {
 }
 
 template <class F, class FS>
-int msm_run(const MsmBases& b, size_t off, size_t n, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
-            MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches) {
-    if (off > b.n || n > b.n - off) { zk_set_error("msm: slice [%zu, %zu) outside the %zu resident bases", off, off + n, b.n); return ZK_ERR_INVALID; }
+int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
+            MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches, const affine_t* d_extra, size_t n_extra) {
+    const size_t n = n_main + n_extra;                // scalars per MSM
+    if (n_extra && !d_extra) { zk_set_error("msm: extra points missing"); return ZK_ERR_INVALID; }
+    if (off > b.n || n_main > b.n - off) { zk_set_error("msm: slice [%zu, %zu) outside the %zu resident bases", off, off + n_main, b.n); return ZK_ERR_INVALID; }
     if (k == 0 || k > MSM_MAX_BATCH) { zk_set_error("msm: batch of %u outside [1, %u]", k, MSM_MAX_BATCH); return ZK_ERR_INVALID; }
     shape->c = 0; shape->groups = 0; shape->batch = k;
     if (n == 0) return ZK_OK;
@@ -502,7 +510,8 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* const* d_scalars,
     const uint32_t B = 1u << (c - 1);                 // buckets per group
     const size_t NB = (size_t)G * B;
     const size_t Mmax = n * nwin * (size_t)k;
-    if (Mmax >= 0x7fffffffull || NB >= 0x7fffffffull || b.n * (size_t)std::max(1u, b.nwin) >= 0x7fffffffull) {
+    const size_t main_count = b.n * (size_t)std::max(1u, b.nwin);   // table entries; the extra points' rows are addressed behind them
+    if (Mmax >= 0x7fffffffull || NB >= 0x7fffffffull || main_count + n_extra * nwin >= 0x7fffffffull) {
         zk_set_error("msm: %zu x %u x %u entries exceed the 31-bit index space", n, nwin, k);
         return ZK_ERR_INVALID;
     }
@@ -597,11 +606,11 @@ int msm_run(const MsmBases& b, size_t off, size_t n, const fe* const* d_scalars,
     STAGE_MARK(2);
     // 3. scatter (counting sort by bucket)
     k_scatter<<<(unsigned)((Mmax + 255) / 256), 256, 0, st>>>(ws.d_digits, n, c, nwin, k, gpm, use_table ? 0 : 1, off, b.n, use_table ? 1 : 0,
-                                                            ws.d_offsets, ws.d_counts, ws.d_entries);
+                                                            n_main, n_extra, (uint32_t)main_count, ws.d_offsets, ws.d_counts, ws.d_entries);
     STAGE_MARK(3);
     // 4. accumulation: one task per <= K sorted entries of one bucket
     k_accumulate<F><<<(unsigned)((NTmax + 127) / 128), 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, ws.d_meta,
-                                                                   ws.d_giants, ws.d_partials);
+                                                                   ws.d_giants, d_extra, (uint32_t)main_count, ws.d_partials);
     STAGE_MARK(4);
     // 5. giants to one slot each, then row / column sums straight from the partial list
     k_giant_finish<F><<<dim3(GIANT_GRID, GIANT_SLICES), TREE_THREADS, 0, st>>>(ws.d_giants, ws.d_meta, ws.d_task_off, ws.d_partials, ws.d_giant_slices,
@@ -661,7 +670,8 @@ template int msm_sum_partials<FqParams>(const xyzz_t*, size_t, size_t, xyzz_t*, 
 
 #define INST(F, FS)                                                                                                             \
     template int msm_bases_create<F>(MsmBases&, const affine_t*, bool, size_t, unsigned, cudaStream_t);                          \
-    template int msm_run<F, FS>(const MsmBases&, size_t, size_t, const fe* const*, unsigned, bool, unsigned, MsmWorkspace&, cudaStream_t, MsmResultShape*, unsigned*);
+    template int msm_run<F, FS>(const MsmBases&, size_t, size_t, const fe* const*, unsigned, bool, unsigned, MsmWorkspace&, cudaStream_t, MsmResultShape*, unsigned*, \
+                                const affine_t*, size_t);
 INST(FpParams, FqParams)  // Pallas: coordinates Fp, scalars Fq
 INST(FqParams, FpParams)  // Vesta:  coordinates Fq, scalars Fp
 #undef INST

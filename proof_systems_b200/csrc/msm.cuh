@@ -97,12 +97,16 @@ struct MsmResultShape {
 // k <= MSM_MAX_BATCH MSMs over bases[off .. off+n) in one pipeline.  d_scalars[j]: the n scalars of MSM j, already on the device
 // (8 u32 each).  window c: 0 = default (ignored when the bases carry a precomputed table).  Synchronises the stream (unless
 // ws.defer_sync / ws.d_T_out); the O(c) tail is finished by the caller.
+// d_extra / n_extra: n_extra further points that belong to this call only (h and the fresh base U of an IPA round,
+// poly-commitment/src/ipa.rs:944,954), laid out like the table — row w holds 2^(c*w) * E_e at d_extra[w * n_extra + e] (one row
+// without a table); every scalar vector then carries n_main + n_extra scalars, the extras' last.
 // out[i] = sum over r < world of all[r * count + i]   (the cross-rank sum of gathered slice sums, i < count)
 template <class F> int msm_sum_partials(const xyzz_t* d_all, size_t world, size_t count, xyzz_t* d_out, cudaStream_t st);
 
 template <class F, class FS>
-int msm_run(const MsmBases& b, size_t off, size_t n, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
-            MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches);
+int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
+            MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches, const affine_t* d_extra = nullptr,
+            size_t n_extra = 0);
 
 // group_ntt.cu: Lagrange-basis commitments of the domain of size 2^log_n from the resident generators (SRS::lagrange_basis)
 template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigned log_n, affine_t* d_out, cudaStream_t st, unsigned* launches);

@@ -18,15 +18,6 @@
 
 using namespace zkb;
 
-struct zk_srs {
-    zk_ctx* ctx = nullptr;
-    int curve = 0;
-    size_t n = 0;                       // |g| = max_poly_size
-    zk_bases* g = nullptr;              // resident generators
-    uint64_t h[8];                      // blinding base
-    std::map<size_t, zk_bases*> lagrange;  // domain size -> resident Lagrange basis (one chunk per element: domain <= |g|)
-};
-
 // SRS::mask_custom (ipa.rs:605-622): chunk_i + blinder_i * h; one scalar multiplication per chunk, host side.
 template <class HP, class HS> static void mask_one(const uint64_t* chunk, const uint64_t* blinder_mont, const uint64_t* h, uint64_t* out) {
     using namespace host;

@@ -134,6 +134,70 @@ class SRS:
         return self.mask_custom(self.commit_evaluations_non_hiding(domain_size, evals), blinders)
 
 
+class OpeningProof:
+    """poly_commitment::ipa::OpeningProof (ipa.rs:1175-1191): lr [rounds, 2, 8], delta [8], z1 [4], z2 [4], sg [8] — points affine,
+    everything in Montgomery limbs"""
+
+    def __init__(self, lr, delta, z1, z2, sg):
+        self.lr, self.delta, self.z1, self.z2, self.sg = lr, delta, z1, z2, sg
+
+
+def srs_open(srs, plnms, elm, polyscale, evalscale, rng_scalars, u_base, round_challenge, final_challenge) -> OpeningProof:
+    """SRS::open (ipa.rs:823-1061) through zk_srs_open.
+    plnms: list of (data [len, 4] Montgomery numpy array OR (device_ptr, len), domain_size (0 = coefficients), blinders [k, 4]);
+    elm [m, 4]; rng_scalars [2 * rounds + 2, 4] = rand_l, rand_r per round, then d, r_delta; the three callables are the caller's
+    transcript: u_base(cip [4]) -> U [8]; round_challenge(i, l [8], r [8]) -> u [4]; final_challenge(delta [8]) -> c [4]."""
+    from ._lib import FINAL_CB, ROUND_CB, U_BASE_CB, OpenPoly, OpenTranscript
+    keep, arr = [], (OpenPoly * max(1, len(plnms)))()
+    for i, (data, dom, blinders) in enumerate(plnms):
+        if isinstance(data, tuple):
+            ptr, ln = data
+        else:
+            d = _np_u64(data, (4,))
+            keep.append(d)
+            ptr, ln = d.ctypes.data, d.shape[0]
+        bl = _np_u64(blinders, (4,))
+        keep.append(bl)
+        arr[i] = OpenPoly(ptr, ln, dom, bl.ctypes.data, bl.shape[0])
+    elm = _np_u64(elm, (4,))
+    rng = _np_u64(rng_scalars, (4,))
+    ps = np.ascontiguousarray(polyscale, dtype=np.uint64).reshape(4)
+    es = np.ascontiguousarray(evalscale, dtype=np.uint64).reshape(4)
+    errors = []
+
+    def view(p, n):
+        return np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+    def put(p, v, n):
+        np.ctypeslib.as_array(p, shape=(n,))[:] = np.ascontiguousarray(v, dtype=np.uint64).reshape(n)
+
+    def guard(fn):
+        def wrapped(*a):
+            try:
+                fn(*a)
+                return 0
+            except Exception as e:           # never unwind through the C frames
+                errors.append(e)
+                return 1
+        return wrapped
+
+    cb_u = U_BASE_CB(guard(lambda user, cip, out: put(out, u_base(view(cip, 4)), 8)))
+    cb_r = ROUND_CB(guard(lambda user, i, l, r, out: put(out, round_challenge(int(i), view(l, 8), view(r, 8)), 4)))
+    cb_f = FINAL_CB(guard(lambda user, d, out: put(out, final_challenge(view(d, 8)), 4)))
+    tr = OpenTranscript(None, cb_u, cb_r, cb_f)
+    rounds_cap = 64
+    lr = np.zeros((rounds_cap, 2, 8), dtype=np.uint64)
+    delta, sg = np.zeros(8, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+    z1, z2 = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+    rounds = ctypes.c_size_t(0)
+    rc = lib().zk_srs_open(srs._h, arr, len(plnms), _ptr(elm), elm.shape[0], _ptr(ps), _ptr(es), _ptr(rng), rng.shape[0], ctypes.byref(tr),
+                           _ptr(lr), rounds_cap, ctypes.byref(rounds), _ptr(delta), _ptr(z1), _ptr(z2), _ptr(sg))
+    if errors:
+        raise errors[0]
+    check(rc)
+    return OpeningProof(lr[: rounds.value].copy(), delta, z1, z2, sg)
+
+
 class IpaRounds:
     """The folding loop of SRS::open (poly-commitment/src/ipa.rs:929-1007) with a and b resident on the device and the bases
     taken from the resident SRS table (`bases` = ctx.upload_bases(curve, srs.g)); see csrc/ipa.cu.

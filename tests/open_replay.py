@@ -174,3 +174,55 @@ def first_opening_proof_bytes(orc, vesta_srs, make_rounds) -> bytes:
     pt = lambda p: b"\xc4\x21" + P.compress(p)
     fe = lambda x: b"\xc4\x20" + x.to_bytes(32, "little")
     return b"\x95" + bytes([0x90 | len(lr)]) + b"".join(b"\x92" + pt(l) + pt(r) for l, r in lr) + pt(delta) + fe(z1) + fe(z2) + pt(g0)
+
+
+def opening_proof_bytes_product_level(orc, zk, ctx, vesta_srs) -> bytes:
+    """The same proof through the PRODUCT-LEVEL entry point zk_srs_open (csrc/open.cu): combine_polys, b_init, the combined inner
+    product, the rounds (h and U inside the MSMs), r_prime, delta, z1, z2 all run in the library; this function only draws the
+    random stream in the reference's order and plays the transcript (sponge, group map, endo challenges) behind the callbacks."""
+    P = Points(orc)
+    g = vesta_srs.g[:SRS_LEN]
+    h = vesta_srs.mont_points(vesta_srs.h_xy_canon)[0]
+    rng = StdRng(bytes(32))
+    elm = [draw_fp(rng) for _ in range(7)]
+    polys = []
+    for _ in range(11):
+        ln = rng.next_u64() % 500
+        coeffs = [draw_fp(rng) for _ in range(ln + 1)] if ln else []
+        chunks = max(1, -(-len(coeffs) // SRS_LEN))
+        polys.append((coeffs, [draw_fp(rng) for _ in range(chunks)]))
+    polyscale, evalscale = draw_fp(rng), draw_fp(rng)
+    draws = [draw_fp(rng) for _ in range(2 * 7 + 2)]                      # rand_l, rand_r per round, then d, r_delta (ipa.rs:936-937, 1027-1028)
+
+    endo_q, endo_r = endo_coefficient(FQ), endo_coefficient(FP)
+    gen = P.from_xy(1, GENERATOR_Y_VESTA)
+    if not np.array_equal(P.mul(gen, endo_r), P.from_xy(endo_q % FQ, GENERATOR_Y_VESTA)):
+        endo_r = endo_r * endo_r % FP
+    mont = lambda xs: orc.to_mont(orc.FP, orc.ints_to_limbs(list(xs))) if len(xs) else np.zeros((0, 4), dtype=np.uint64)
+    fe_int = lambda limbs: orc.fe_int(orc.FP, np.ascontiguousarray(limbs, dtype=np.uint64).reshape(4))
+    sponge = DefaultFqSponge("fq")
+
+    def u_base(cip):
+        sponge.absorb_fr([(fe_int(cip) - (pow(2, 255, FP) + 1)) * pow(2, -1, FP) % FP])      # shift_scalar (commitment.rs:273-288)
+        return P.from_xy(*BWGroupMap(FQ).to_group(sponge.challenge_fq()))
+
+    def round_challenge(i, l, r):
+        sponge.absorb_g([P.xy(l)])
+        sponge.absorb_g([P.xy(r)])
+        return mont([scalar_challenge_to_field(sponge.challenge(), endo_r, FP)])[0]
+
+    def final_challenge(delta):
+        sponge.absorb_g([P.xy(delta)])
+        return mont([scalar_challenge_to_field(sponge.challenge(), endo_r, FP)])[0]
+
+    srs = zk.SRS(ctx, zk.VESTA, g, h)
+    try:
+        plnms = [(mont(c), 0, mont(bl)) for c, bl in polys]
+        proof = zk.srs_open(srs, plnms, mont(elm), mont([polyscale])[0], mont([evalscale])[0], mont(draws), u_base, round_challenge, final_challenge)
+    finally:
+        srs.close()
+    pt = lambda p: b"\xc4\x21" + P.compress(p)
+    fe = lambda x: b"\xc4\x20" + fe_int(x).to_bytes(32, "little")
+    lr = proof.lr
+    return (b"\x95" + bytes([0x90 | len(lr)]) + b"".join(b"\x92" + pt(l) + pt(r) for l, r in lr) + pt(proof.delta) + fe(proof.z1) + fe(proof.z2)
+            + pt(proof.sg))

@@ -260,3 +260,72 @@ def test_opening_proof_serialization_regression_bytes_on_device(ctx, orc, vesta_
     raw = first_opening_proof_bytes(orc, vesta_srs, lambda g, a, b: DeviceRounds(orc, zk, ctx, g, a, b))
     want = json.load(open(GOLDEN))["opening_proof_vesta_srs128"]
     assert padded(raw, len(want)) == want
+
+
+def test_opening_proof_regression_bytes_through_zk_srs_open(ctx, orc, vesta_srs):
+    """The same regression (commitment.rs:388-443) through the PRODUCT-LEVEL entry point zk_srs_open (csrc/open.cu): combine_polys,
+    b_init, the combined inner product, the rounds with h and U inside the MSMs, r_prime, delta, z1 and z2 are all computed by the
+    library; the test only plays the transcript (sponge, group map) behind the callbacks and serialises the result."""
+    import json
+
+    from open_replay import opening_proof_bytes_product_level
+    from test_ser_regression import GOLDEN, padded
+    raw = opening_proof_bytes_product_level(orc, zk, ctx, vesta_srs)
+    want = json.load(open(GOLDEN))["opening_proof_vesta_srs128"]
+    assert padded(raw, len(want)) == want
+
+
+@pytest.mark.parametrize("window_bits", [-1, 0])
+def test_open_evaluation_form_and_chunked_inputs(ctx, orc, pallas_srs, window_bits):
+    """combine_polys (poly-commitment/src/utils.rs:103-202) on the device: evaluation-form entries (sub-sampled, interpolated, chunked
+    and linearised with powers of polyscale starting at 1, utils.rs:183-199) must give the proof of the equivalent
+    coefficient-form batch; chunked coefficient-form entries and a non power-of-two SRS (padding, ipa.rs:848-862) are in the mix.
+    The transcript behind the callbacks is a deterministic stand-in: equality of two library runs is what is checked, plus
+    sg = <b_poly_coefficients(chals), g> and the verifier's z1 / z2 identity against the oracle."""
+    G = pallas_srs
+    fs, srs_len, dom = G.scalar, 48, 128
+    m = orc.MODULUS[fs]
+    ints = lambda a: orc.limbs_to_ints(orc.from_mont(fs, np.ascontiguousarray(a).reshape(-1, 4)))
+    mont = lambda xs: orc.to_mont(fs, orc.ints_to_limbs([x % m for x in xs])) if len(xs) else np.zeros((0, 4), dtype=np.uint64)
+    rnd = lambda k, seed: orc.to_mont(fs, orc.random_scalars(fs, k, seed=seed))
+    srs = zk.SRS(ctx, G.cid, G.g[:srs_len], G.mont_points(G.h_xy_canon)[0], window_bits=window_bits)
+    rounds = 6                                                            # ceil_log2(48)
+    polyscale, evalscale = rnd(1, 1)[0], rnd(1, 2)[0]
+    ps = ints(polyscale)[0]
+    elm, draws = rnd(3, 3), rnd(2 * rounds + 2, 4)
+    ev = rnd(4 * dom, 5)                                                  # evaluations on a 4x larger domain: stride 4
+    ev_bl, dense, dense_bl = rnd(3, 6), rnd(100, 7), rnd(3, 8)            # domain 128 over |g| = 48: 3 chunks each
+    chals = []
+
+    def transcript():
+        chals.clear()
+        state = [7]
+
+        def nxt():
+            state[0] = (state[0] * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+            return state[0]
+        u_base = lambda cip: G.g[100 + int(ints(cip)[0] % 50)]           # any curve point
+        def rc(i, l, r):
+            u = mont([nxt() * (1 << 64) + nxt() + ints(l[:4])[0] % 3])[0]
+            chals.append(ints(u)[0])
+            return u
+        fc = lambda delta: mont([nxt() + 1])[0]
+        return u_base, rc, fc
+
+    proof_e = zk.srs_open(srs, [(dense, 0, dense_bl), (ev, dom, ev_bl)], elm, polyscale, evalscale, draws, *transcript())
+    # the equivalent batch in coefficient form: the interpolated, chunk-linearised polynomial in the evaluation entry's place,
+    # followed by empty entries that advance the scale like its remaining chunks (utils.rs:151-164)
+    coeffs = ints(orc.ntt(fs, np.ascontiguousarray(ev[::4]), inverse=True))
+    lin = [sum(pow(ps, k, m) * (coeffs[k * srs_len + i] if k * srs_len + i < dom else 0) for k in range(3)) % m for i in range(srs_len)]
+    empty = np.zeros((0, 4), dtype=np.uint64)
+    proof_c = zk.srs_open(srs, [(dense, 0, dense_bl), (mont(lin), 0, ev_bl[:1]), (empty, 0, ev_bl[1:2]), (empty, 0, ev_bl[2:3])], elm, polyscale,
+                          evalscale, draws, *transcript())
+    for a, b in ((proof_e.lr, proof_c.lr), (proof_e.delta, proof_c.delta), (proof_e.z1, proof_c.z1), (proof_e.z2, proof_c.z2), (proof_e.sg, proof_c.sg)):
+        assert np.array_equal(a, b)
+    assert proof_e.lr.shape == (rounds, 2, 8) and np.any(proof_e.lr[-1])
+    # sg = <b_poly_coefficients(chals), g> (commitment.rs:565-581), an MSM the oracle can redo
+    s = [1]
+    for u in chals:
+        s = [v for t in s for v in (t, t * u % m)]
+    assert np.array_equal(proof_e.sg, orc.msm(G.cid, G.g[:srs_len], orc.ints_to_limbs(s[:srs_len])))
+    srs.close()

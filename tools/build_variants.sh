@@ -8,7 +8,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 for spec in "$@"; do
   tag=${spec%%:*}; flags=${spec#*:}
   dir=/tmp/zkb_build_$tag; mkdir -p $dir
-  for f in api msm ntt srs group_ntt decompress ipa $EXTRA_SRCS; do
+  for f in api msm ntt srs group_ntt decompress ipa open $EXTRA_SRCS; do
     [ -f $f.cu ] || continue
     $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -ccbin /usr/bin/g++ \
       --expt-relaxed-constexpr $flags -c -o $dir/$f.o $f.cu &
