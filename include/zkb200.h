@@ -91,6 +91,11 @@ int zk_points_decompress(zk_ctx* ctx, int curve_id, const uint8_t* in33, size_t 
 int zk_points_from_uncompressed(zk_ctx* ctx, int curve_id, const uint8_t* in65, size_t n, uint64_t* out_xy);
 int zk_points_compress(zk_ctx* ctx, int curve_id, const uint64_t* xy_mont, size_t n, uint8_t* out33);
 
+/* Synthetic on-curve points for workloads larger than the 2^16 generators the reference ships (BASELINE config 4): point i is
+ * a deterministic function of (curve_id, seed, i) — try-and-increment on x until x^3 + 5 is a square (csrc/decompress.cu).
+ * Benchmark / test input only: the points have no known relation to the SRS generators. */
+int zk_points_synthetic(zk_ctx* ctx, int curve_id, uint64_t seed, size_t n, uint64_t* out_xy);
+
 /* ------------------------------------------------------------------ MSM
  * zk_msm == <G::Group as VariableBaseMSM>::msm_bigint(&bases[off..off+n], scalars)   (scalars_are_mont = 0: canonical
  *           integers, poly-commitment/src/ipa.rs:672,943,953; commitment.rs:382,387)

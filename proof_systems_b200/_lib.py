@@ -97,6 +97,9 @@ def lib() -> ctypes.CDLL:
     L.zk_debug_mul_throughput.argtypes = [vp, i, u, ctypes.POINTER(ctypes.c_double)]
     L.zk_debug_op_throughput.argtypes = [vp, i, i, u, u, u, ctypes.POINTER(ctypes.c_double)]
     _lib = L
+    if os.environ.get("ZKB200_LIB") and not hasattr(L, "zk_points_synthetic"):
+        return L      # an A/B build of an older tree (tools/build_variants.sh): the newest entry points are absent
+    L.zk_points_synthetic.argtypes = [vp, i, ctypes.c_uint64, sz, vp]
     L.zk_srs_open.argtypes = [vp, ctypes.POINTER(OpenPoly), sz, vp, sz, vp, vp, vp, sz, ctypes.POINTER(OpenTranscript), vp, sz,
                               ctypes.POINTER(sz), vp, vp, vp, vp]
     return L
@@ -214,6 +217,12 @@ class Context:
         pts = _np_u64(points, (8,))
         out = np.zeros((pts.shape[0], 33), dtype=np.uint8)
         check(lib().zk_points_compress(self._h, curve, _ptr(pts), pts.shape[0], _ptr(out)))
+        return out
+
+    def synthetic_points(self, curve: int, n: int, seed: int = 0) -> np.ndarray:
+        """n deterministic on-curve points [n, 8] (zk_points_synthetic): inputs for workloads larger than the shipped SRS"""
+        out = np.empty((n, 8), dtype=np.uint64)
+        check(lib().zk_points_synthetic(self._h, curve, ctypes.c_uint64(seed), n, out.ctypes.data_as(_u64p)))
         return out
 
     def upload_bases(self, curve: int, points, window_bits: int = -1) -> "Bases":

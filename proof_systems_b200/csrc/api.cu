@@ -17,6 +17,7 @@ namespace zkb {
 template <class F> int points_decompress(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st);   // decompress.cu
 template <class F> int points_from_uncompressed(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st);
 template <class F> int points_compress(const affine_t* d_in, uint8_t* d_out, size_t n, cudaStream_t st);
+template <class F> int points_synthetic(affine_t* d_out, size_t n, uint64_t seed, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 void zk_set_error(const char* fmt, ...) {
@@ -401,6 +402,26 @@ int zk_points_from_uncompressed(zk_ctx* ctx, int curve_id, const uint8_t* in65, 
 }
 int zk_points_compress(zk_ctx* ctx, int curve_id, const uint64_t* xy_mont, size_t n, uint8_t* out33) {
     return points_codec(ctx, curve_id, 2, xy_mont, n, out33, "points_compress");
+}
+
+int zk_points_synthetic(zk_ctx* ctx, int curve_id, uint64_t seed, size_t n, uint64_t* out_xy) {
+    if (!ctx || (!out_xy && n)) { zk_set_error("points_synthetic: null argument"); return ZK_ERR_INVALID; }
+    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("points_synthetic: unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return ZK_OK;
+    affine_t* d = nullptr;
+    ZK_CUDA(cudaMalloc(&d, n * sizeof(affine_t)));
+    int rc = curve_id == ZK_PALLAS ? points_synthetic<FpParams>(d, n, seed, ctx->stream) : points_synthetic<FqParams>(d, n, seed, ctx->stream);
+    cudaError_t e = cudaSuccess;
+    if (rc == ZK_OK) {
+        ctx->launches += 1;
+        e = cudaMemcpyAsync(out_xy, d, n * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) { zk_set_error("points_synthetic: %s", cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------- MSM

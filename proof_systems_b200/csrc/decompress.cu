@@ -143,6 +143,44 @@ template <class F> __global__ void __launch_bounds__(128) k_compress(const affin
     p[32] = fe_canonical_gt<F>(a.y, fe_neg<F>(a.y)) ? 0x80 : 0x00;
 }
 
+// Synthetic on-curve points for benchmarks and tests that need more bases than the reference ships (BASELINE config 4: 2^20
+// points; srs/*.srs hold 2^16): point i = the first x in the sequence H(seed, i, 0), H(seed, i, 1), ... (splitmix64 words, below
+// 2^254, read as a Montgomery residue) for which x^3 + 5 is a square, with the root Tonelli-Shanks returns.  Deterministic in
+// (curve, seed, i); about two attempts per point.
+template <class F> __global__ void __launch_bounds__(128) k_synthetic_points(affine_t* out, size_t n, uint64_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe five = fe_zero();
+    five.v[0] = 5;
+    const fe b = fe_to_mont<F>(five);
+    for (uint64_t attempt = 0;; attempt++) {
+        fe x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint64_t z = seed + 0x9E3779B97F4A7C15ull * (4 * (uint64_t)i + k + 1) + 0xD1B54A32D192ED03ull * attempt;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            if (k == 3) z &= (1ull << 62) - 1;
+            x.v[2 * k] = (uint32_t)z; x.v[2 * k + 1] = (uint32_t)(z >> 32);
+        }
+        fe y;
+        if (fe_sqrt<F>(fe_add<F>(fe_mul<F>(fe_sqr<F>(x), x), b), y) && !fe_is_zero(y)) {
+            affine_t r;
+            r.x = x; r.y = y;
+            store_affine(out + i, r);
+            return;
+        }
+    }
+}
+template <class F> int points_synthetic(affine_t* d_out, size_t n, uint64_t seed, cudaStream_t st) {
+    if (n) k_synthetic_points<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_out, n, seed);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+template int points_synthetic<FpParams>(affine_t*, size_t, uint64_t, cudaStream_t);
+template int points_synthetic<FqParams>(affine_t*, size_t, uint64_t, cudaStream_t);
+
 template <class F> int points_from_uncompressed(const uint8_t* d_in, affine_t* d_out, size_t n, unsigned* d_bad, cudaStream_t st) {
     ZK_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), st));
     if (n) k_from_uncompressed<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_in, d_out, n, d_bad);

@@ -31,6 +31,38 @@ template <class F> __global__ void k_build_table(affine_t* table, size_t n, unsi
     }
 }
 
+// The same table with ONE field inversion per point instead of one per row (Montgomery's trick over the rows of a point):
+// ~255 doublings + 1 inversion + 8 multiplications per row, 3.4x less arithmetic than k_build_table.  nwin <= TABLE_MAX_ROWS.
+constexpr unsigned TABLE_MAX_ROWS = 33;   // windows of >= 8 bits
+template <class F> __global__ void __launch_bounds__(128) k_build_table_batched(affine_t* table, size_t n, unsigned c, unsigned nwin) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const affine_t p = load_affine_nc(table + i);
+    if (affine_is_inf(p)) {
+        for (unsigned w = 1; w < nwin; w++) store_affine(table + (size_t)w * n + i, p);
+        return;
+    }
+    xyzz_t pts[TABLE_MAX_ROWS];
+    fe pre[TABLE_MAX_ROWS];
+    xyzz_t acc = xyzz_from_affine<F>(p);
+    for (unsigned w = 1; w < nwin; w++) {
+        for (unsigned k = 0; k < c; k++) acc = xyzz_dbl<F>(acc);
+        pts[w] = acc;
+        const fe z = fe_mul<F>(acc.ZZ, acc.ZZZ);        // never zero: the curve has prime order, doubling a finite point stays finite
+        pre[w] = w == 1 ? z : fe_mul<F>(pre[w - 1], z);
+    }
+    if (nwin < 2) return;
+    fe inv = fe_inv<F>(pre[nwin - 1]);
+    for (unsigned w = nwin - 1; w >= 1; w--) {
+        const fe zi = w == 1 ? inv : fe_mul<F>(inv, pre[w - 1]);          // 1 / (ZZ_w * ZZZ_w)
+        inv = fe_mul<F>(inv, fe_mul<F>(pts[w].ZZ, pts[w].ZZZ));
+        affine_t r;
+        r.x = fe_mul<F>(pts[w].X, fe_mul<F>(zi, pts[w].ZZZ));              // X / ZZ
+        r.y = fe_mul<F>(pts[w].Y, fe_mul<F>(zi, pts[w].ZZ));               // Y / ZZZ
+        store_affine(table + (size_t)w * n + i, r);
+    }
+}
+
 template <class F> int msm_bases_create(MsmBases& b, const affine_t* pts, bool pts_on_device, size_t n, unsigned c_table, cudaStream_t st) {
     if (c_table > MSM_MAX_WINDOW_BITS) { zk_set_error("msm: table window %u > %u", c_table, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
     b.n = n;
@@ -41,7 +73,8 @@ template <class F> int msm_bases_create(MsmBases& b, const affine_t* pts, bool p
     if (n == 0) return ZK_OK;
     ZK_CUDA(cudaMemcpyAsync(b.d_points, pts, n * sizeof(affine_t), pts_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     if (c_table) {
-        k_build_table<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b.d_points, n, c_table, b.nwin);
+        if (b.nwin <= TABLE_MAX_ROWS) k_build_table_batched<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b.d_points, n, c_table, b.nwin);
+        else k_build_table<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b.d_points, n, c_table, b.nwin);
         ZK_CUDA(cudaGetLastError());
     }
     ZK_CUDA(cudaStreamSynchronize(st));
@@ -60,7 +93,7 @@ void msm_bases_free(MsmBases& b) {
 template <class FS>
 __global__ void k_recode(MsmScalarSet sc, int scalars_mont, size_t n, unsigned c, unsigned nwin, unsigned gpm, int per_window,
                          int32_t* digits, uint32_t* counts, uint32_t* meta) {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { meta[2] = 0; meta[4] = 0; }   // giants, plan tiles done
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) meta[2] = 0;   // giant list of this run (k_plan)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned j = blockIdx.y;
@@ -95,8 +128,7 @@ __global__ void k_recode(MsmScalarSet sc, int scalars_mont, size_t n, unsigned c
 // spins on tile t-1's published inclusive total — tiles are dispatched in order, so the predecessor is always resident), which
 // keeps the scan a single launch for any batch size.  64-bit lanes carry (entry count << 32 | task count): one scan yields both.
 // Buckets with more than smax tasks ("giant": the all-ones witness columns of kimchi put ~n entries in one bucket,
-// SURVEY.md §3.1) are listed; the last tile to finish lays out their side areas behind the main slots.  Clears counts
-// (re-used as scatter cursors).
+// SURVEY.md §3.1) are listed for k_giant_finish.  Clears counts (re-used as scatter cursors).
 __device__ __forceinline__ uint64_t block_excl_scan_1024(uint64_t v, uint64_t* warp_sums, uint64_t* tile_total) {
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint64_t x = v;
@@ -128,7 +160,6 @@ __global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offse
                                                  uint32_t* meta, uint32_t* giants, uint64_t* chain, uint32_t* chain_flag, uint32_t epoch) {
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t tile_total, prefix_s;
-    __shared__ uint32_t last_s;
     const unsigned tid = threadIdx.x, tile = blockIdx.x;
     const uint32_t i0 = tile * PLAN_TILE + tid * PLAN_PER_THREAD;
     uint32_t v[PLAN_PER_THREAD];
@@ -163,7 +194,7 @@ __global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offse
             task_off[i0 + k] = (uint32_t)ex;
             if ((uint32_t)pk[k] > smax) {
                 uint32_t gi = atomicAdd(&meta[2], 1u);
-                if (gi < MSM_MAX_GIANTS) { giants[gi] = i0 + k; giants[MSM_MAX_GIANTS + gi] = (uint32_t)pk[k]; }
+                if (gi < MSM_MAX_GIANTS) giants[gi] = i0 + k;
             }
         }
         ex += pk[k];
@@ -172,21 +203,6 @@ __global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offse
         const uint64_t tot = prefix_s + tile_total;
         offsets[nb] = (uint32_t)(tot >> 32); task_off[nb] = (uint32_t)tot;
         meta[0] = (uint32_t)(tot >> 32); meta[1] = (uint32_t)tot;
-    }
-    // the last tile to finish sees the complete giant list: main slots first, then one side area per listed giant
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) last_s = atomicAdd(&meta[4], 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (last_s && tid == 0) {
-        __threadfence();
-        const uint32_t ng = min(*(volatile uint32_t*)(meta + 2), MSM_MAX_GIANTS);
-        const uint32_t nt = (uint32_t)(*(volatile uint64_t*)(chain + (gridDim.x - 1)));
-        uint32_t excess = 0;
-        for (uint32_t r = 0; r < ng; r++) excess += *(volatile uint32_t*)(giants + MSM_MAX_GIANTS + r) - 1;
-        uint32_t base = nt - excess;
-        meta[3] = base;
-        for (uint32_t r = 0; r < ng; r++) { giants[2 * MSM_MAX_GIANTS + r] = base; base += *(volatile uint32_t*)(giants + MSM_MAX_GIANTS + r); }
     }
 }
 
@@ -216,38 +232,15 @@ __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned 
     entries[pos] = (uint32_t)pidx | (sd < 0 ? 0x80000000u : 0u);
 }
 
-// ---------------------------------------------------------------------------------------------- slots of the partial list
-// Task t of bucket b leaves its partial in a SLOT.  Main slots follow bucket order: bucket b owns [slot_of(b), slot_of(b+1));
-// that is its task range, except that a listed giant owns ONE main slot (its total, written by k_giant_finish) and keeps its
-// task partials in a side area behind the main slots.  With no giants (uniform scalars) slot == task index.
-struct GiantList {
-    const uint32_t* bucket;   // [ng]
-    const uint32_t* tasks;    // [ng]
-    const uint32_t* area;     // [ng] first slot of the side area
-    uint32_t ng;
-};
-__device__ __forceinline__ GiantList giant_list(const uint32_t* __restrict__ meta, const uint32_t* __restrict__ giants) {
-    GiantList g;
-    g.ng = min(__ldg(meta + 2), MSM_MAX_GIANTS);
-    g.bucket = giants; g.tasks = giants + MSM_MAX_GIANTS; g.area = giants + 2 * MSM_MAX_GIANTS;
-    return g;
-}
-__device__ __forceinline__ uint32_t slot_of(const uint32_t* __restrict__ task_off, uint32_t b, const GiantList& g) {
-    uint32_t s = __ldg(task_off + b);
-    for (uint32_t r = 0; r < g.ng; r++)
-        if (__ldg(g.bucket + r) < b) s -= __ldg(g.tasks + r) - 1;
-    return s;
-}
-
 // ---------------------------------------------------------------------------------------------- accumulation
 // Task t belongs to the bucket b with task_off[b] <= t < task_off[b+1]; the bucket's n_b sorted entries are cut into
 // s_b = ceil(n_b / K) nearly equal parts, so no task crosses a bucket boundary and every thread sums <= K points with
-// XYZZ mixed additions and leaves one partial in its slot.
+// XYZZ mixed additions.  Single-task buckets are written directly, the others leave one partial per task.
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__ points, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
-                                                    uint32_t K, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ giants,
-                                                    const affine_t* __restrict__ extra, uint32_t main_count, xyzz_t* partials) {
+                                                    uint32_t K, const uint32_t* __restrict__ meta, const affine_t* __restrict__ extra,
+                                                    uint32_t main_count, xyzz_t* buckets, xyzz_t* partials) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= __ldg(meta + 1)) return;
     // upper_bound(task_off[0..nb], t) - 1
@@ -279,186 +272,193 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
         if (sign) q.y = fe_neg<F>(q.y);
         acc = xyzz_madd<F>(acc, q);
     }
-    uint32_t dest = t;
-    const GiantList g = giant_list(meta, giants);
-    if (g.ng) {
-        uint32_t excess = 0, mine = 0xffffffffu;
-        for (uint32_t r = 0; r < g.ng; r++) {
-            const uint32_t gb = __ldg(g.bucket + r);
-            if (gb < b) excess += __ldg(g.tasks + r) - 1;
-            else if (gb == b) mine = r;
+    store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
+}
+
+// Balanced first level of the per-bucket sums.  The task partials lie in bucket order; thread u sums the RUN of `run`
+// consecutive partials [u*run, (u+1)*run) segment by segment (a segment = the part of one bucket inside the run) and writes each
+// segment sum back at the segment's first index.  Every thread executes at most run-1 additions whatever the bucket sizes, so a
+// warp never waits for its longest bucket.  k_bucket_finish_serial then adds, per bucket, the partial at the bucket's first index
+// and those at the multiples of `run` inside it.  (Slots of single-task buckets hold no partial — k_accumulate wrote the bucket
+// itself — and are segments of their own: read and written back, never mixed.)
+template <class F>
+__global__ void __launch_bounds__(128) k_run_sum(const uint32_t* __restrict__ task_off, uint32_t nb, const uint32_t* __restrict__ meta, uint32_t run,
+                                                 uint32_t smax, xyzz_t* partials) {
+    const uint32_t nt = meta[1];
+    const uint64_t i0w = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * run;
+    if (i0w >= nt) return;
+    const uint32_t i0 = (uint32_t)i0w, i1 = min(nt, i0 + run);
+    // largest b with task_off[b] <= i0 (skips the empty buckets that share a start)
+    uint32_t lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(task_off + mid) <= i0) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo, nxt = __ldg(task_off + b + 1), seg = i0;
+    // giant buckets were summed by k_giant_finish: their slots are skipped (a thread wholly inside one does nothing)
+    const bool giants_done = meta[2] <= MSM_MAX_GIANTS;
+    bool skip = giants_done && nxt - __ldg(task_off + b) > smax;
+    if (skip && nxt >= i1) return;
+    xyzz_t acc = load_xyzz(partials + i0);
+    bool dirty = false;
+    for (uint32_t i = i0 + 1; i < i1; i++) {
+        if (skip && i != nxt) continue;
+        const xyzz_t v = load_xyzz(partials + i);
+        if (i == nxt) {
+            if (dirty) store_xyzz(partials + seg, acc);
+            // the bucket that starts at i: usually the next one; behind a stretch of empty buckets, found by bisection
+            b++; nxt = __ldg(task_off + b + 1);
+            if (nxt <= i) {
+                uint32_t l2 = b, h2 = nb;
+                while (h2 - l2 > 1) {
+                    const uint32_t mid = (l2 + h2) >> 1;
+                    if (__ldg(task_off + mid) <= i) l2 = mid; else h2 = mid;
+                }
+                b = l2; nxt = __ldg(task_off + b + 1);
+            }
+            skip = giants_done && nxt - i > smax;
+            seg = i; acc = v; dirty = false;
+        } else {
+            acc = xyzz_add<F, true>(acc, v);
+            dirty = true;
         }
-        dest = mine != 0xffffffffu ? __ldg(g.area + mine) + sub : t - excess;
     }
-    store_xyzz(partials + dest, acc);
+    if (dirty) store_xyzz(partials + seg, acc);
 }
 
-// ---------------------------------------------------------------------------------------------- sums of partials
-constexpr unsigned TREE_THREADS = 256;              // 64 quads per CTA in the giant / final kernels
+// Thread-per-bucket finish pass, for MANY buckets with few partials each: with more buckets than resident quads the pass is
+// throughput-bound and the quad-cooperative variant below only adds work.  run == 0: the bucket's partials are summed one by
+// one; run > 0: k_run_sum ran first and the bucket's value is spread over its first slot and the multiples of `run` inside it.
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_finish_serial(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
+                                                              uint32_t K, uint32_t smax, const uint32_t* __restrict__ meta, uint32_t run, xyzz_t* buckets,
+                                                              const xyzz_t* __restrict__ partials) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t nbk = __ldg(offsets + b + 1) - __ldg(offsets + b);
+    uint32_t sb = (nbk + K - 1) / K;
+    if (sb > smax && meta[2] <= MSM_MAX_GIANTS) return;  // k_giant_finish
+    if (sb < 2) return;                                  // 0: empty, 1: written by k_accumulate
+    const uint32_t a = __ldg(task_off + b);
+    xyzz_t acc = load_xyzz(partials + a);
+    if (run == 0) {
+        for (uint32_t j = 1; j < sb; j++) acc = xyzz_add<F, true>(acc, load_xyzz(partials + a + j));
+    } else {
+        for (uint32_t k = (a / run + 1) * run; k < a + sb; k += run) acc = xyzz_add<F, true>(acc, load_xyzz(partials + k));
+    }
+    store_xyzz(buckets + b, acc);
+}
+
+// Buckets with 2 <= s_b <= smax tasks: a group of G = 2^log_g QUADS (quad.cuh) sums the bucket's partials — strided serial
+// part, then a shuffle tree over the quads of the group.  One quad per bucket when buckets hold only a few partials.
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_finish(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
+                                                       uint32_t K, uint32_t smax, unsigned log_g, const uint32_t* __restrict__ meta,
+                                                       xyzz_t* buckets, const xyzz_t* __restrict__ partials) {
+    const uint32_t gq = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // global quad
+    const uint32_t G = 1u << log_g, b = gq >> log_g, gl = gq & (G - 1);
+    uint32_t sb = 0, t0 = 0;
+    if (b < nb) {
+        const uint32_t nbk = __ldg(offsets + b + 1) - __ldg(offsets + b);
+        sb = (nbk + K - 1) / K;
+        t0 = __ldg(task_off + b);
+        // giants are left to k_giant_finish — unless their list overflowed, then they are summed here (slow, correct)
+        if (sb > smax && meta[2] <= MSM_MAX_GIANTS) sb = 0;
+        if (sb < 2) sb = 0;
+    }
+    // warp-uniform trip count: every lane must take part in the quad additions' shuffles
+    const unsigned my_trips = sb > gl ? (sb - gl + G - 1) / G : 0;
+    const unsigned trips = __reduce_max_sync(0xffffffffu, my_trips);
+    xyzz_t acc = xyzz_identity();
+    for (unsigned k = 0; k < trips; k++) {
+        const uint32_t j = gl + k * G;
+        xyzz_t o = j < sb ? load_xyzz(partials + t0 + j) : xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+#pragma unroll 1
+    for (unsigned d = G >> 1; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
+        if (gl >= d) o = xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    if (gl == 0 && sb && (threadIdx.x & 3) == 0) store_xyzz(buckets + b, acc);
+}
+
+// ---------------------------------------------------------------------------------------------- bucket reduction
+// sum_b (b+1) * B[b] = sum_t 2^t * T_t,  T_t = sum of B[b] over the b with bit t of (b+1) set.
+// grid (blocks_per_bit, c, G); every CTA tree-sums its slice of one group's buckets for one bit.
+constexpr unsigned TREE_THREADS = 256;              // 64 quads per CTA in the reduction kernels
 constexpr unsigned TREE_QUADS = TREE_THREADS / 4;
-constexpr unsigned ROWCOL_THREADS = 128;            // 32 quads per row / column CTA: the whole grid of a single MSM is one wave
 
-// Block-wide sum of one value per QUAD (replicated in its four lanes; quad.cuh): three shuffle levels inside every warp, one
-// shared-memory hand-over, then the warps' sums in warp 0.  One barrier instead of one per level.  blockDim.x a multiple of 32,
-// <= 1024; sm holds blockDim.x / 32 points.  Result valid in quad 0 of warp 0.
-template <class F> __device__ __forceinline__ xyzz_t block_sum_quads(xyzz_t acc, xyzz_t* sm) {
-    const unsigned tid = threadIdx.x, lane = tid & 31, qw = lane >> 2, wid = tid >> 5, nw = blockDim.x >> 5;
-#pragma unroll 1
-    for (unsigned d = 4; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
-        if (qw >= d) o = xyzz_identity();
-        acc = xyzz_add_quad<F>(acc, o);
-    }
-    if (nw == 1) return acc;
-    if (lane == 0) store_xyzz(sm + wid, acc);
-    __syncthreads();
-    if (wid != 0) return acc;
-    acc = qw < nw ? load_xyzz(sm + qw) : xyzz_identity();
-    unsigned top = 1;
-    while (top < nw) top <<= 1;      // nw <= 8 here; a 32-warp block would need a second hand-over
-#pragma unroll 1
-    for (unsigned d = top >> 1; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, 4 * d);
-        if (qw >= d) o = xyzz_identity();
-        acc = xyzz_add_quad<F>(acc, o);
-    }
-    return acc;
-}
-
-// GIANT_SLICES CTAs per listed giant bucket: each sums a contiguous slice of the giant's side area (quads stride over it, then
-// the block sum); the last CTA to arrive (ticket counter) adds the slice sums and writes the giant's main slot.
-constexpr unsigned GIANT_SLICES = 16, GIANT_GRID = 32;
+// GIANT_SLICES CTAs per giant bucket: each sums a contiguous slice of the bucket's partial list (quads stride over it, then
+// the block tree, quad.cuh); the last CTA to arrive (ticket counter) adds the slice sums and writes the bucket.
+constexpr unsigned GIANT_SLICES = 16;
 template <class F>
 __global__ void __launch_bounds__(TREE_THREADS) k_giant_finish(const uint32_t* __restrict__ giants, const uint32_t* __restrict__ meta,
-                                                               const uint32_t* __restrict__ task_off, xyzz_t* partials, xyzz_t* slice_sums,
+                                                               const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t K,
+                                                               xyzz_t* buckets, const xyzz_t* __restrict__ partials, xyzz_t* slice_sums,
                                                                uint32_t* tickets) {
-    __shared__ xyzz_t sm_tree[TREE_THREADS / 32];
+    extern __shared__ xyzz_t sm_tree[];
     __shared__ uint32_t ticket_s;
-    const GiantList g = giant_list(meta, giants);
+    const uint32_t ng = meta[2];
+    if (ng > MSM_MAX_GIANTS || blockIdx.x >= ng) return;  // overflow: k_bucket_finish took them
+    const uint32_t b = giants[blockIdx.x];
+    const uint32_t nbk = offsets[b + 1] - offsets[b], sb = (nbk + K - 1) / K, t0 = task_off[b];
+    const uint32_t per = (sb + GIANT_SLICES - 1) / GIANT_SLICES;
+    const uint32_t j_lo = blockIdx.y * per, j_hi = min(sb, j_lo + per);
     const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
-    for (uint32_t r = blockIdx.x; r < g.ng; r += gridDim.x) {
-        const uint32_t sb = __ldg(g.tasks + r), t0 = __ldg(g.area + r);
-        const uint32_t per = (sb + GIANT_SLICES - 1) / GIANT_SLICES;
-        const uint32_t j_lo = min(sb, blockIdx.y * per), j_hi = min(sb, j_lo + per);
-        xyzz_t acc = xyzz_identity();
-        for (uint32_t j0 = j_lo; j0 < j_hi; j0 += nq) {
-            xyzz_t o = j0 + qd < j_hi ? load_xyzz(partials + t0 + j0 + qd) : xyzz_identity();
-            acc = xyzz_add_quad<F>(acc, o);
-        }
-        acc = block_sum_quads<F>(acc, sm_tree);
-        xyzz_t* mine = slice_sums + (size_t)r * GIANT_SLICES;
-        if (threadIdx.x == 0) {
-            store_xyzz(mine + blockIdx.y, acc);
-            __threadfence();
-            ticket_s = atomicAdd(&tickets[r], 1u);
-        }
-        __syncthreads();
-        if (ticket_s == GIANT_SLICES - 1) {
-            __threadfence();
-            acc = qd < GIANT_SLICES ? load_xyzz(mine + qd) : xyzz_identity();
-            __syncthreads();   // sm_tree is reused
-            acc = block_sum_quads<F>(acc, sm_tree);
-            if (threadIdx.x == 0) { store_xyzz(partials + slot_of(task_off, __ldg(g.bucket + r), g), acc); tickets[r] = 0; }
-        }
-        __syncthreads();
-    }
-}
-
-// Row and column sums of the (B/W + 1) x W grid of bucket weights i = b + 1 = hi * W + lo, W = 2^w_lo, straight from the
-// partial list:   sum_i i * B[i] = W * sum_hi hi * R[hi] + sum_lo lo * C[lo],   R[hi] = sum of the partials of row hi's buckets (one
-// contiguous slot range), C[lo] = sum of the partials of the buckets hi * W + lo over hi (their slot ranges walked as one flat
-// list, so the quads of a CTA share the work evenly whatever the bucket sizes).  One CTA per row and per column and group;
-// about 2 additions per partial in total, <= ceil(slots / quads) dependent additions per quad plus the block sum.
-constexpr unsigned ROWCOL_MAX_ROWS = 260;           // B / W + 1 <= 257 for c <= 17
-template <class F>
-__global__ void __launch_bounds__(ROWCOL_THREADS) k_rowcol(const xyzz_t* __restrict__ partials, const uint32_t* __restrict__ task_off,
-                                                           const uint32_t* __restrict__ meta, const uint32_t* __restrict__ giants, uint32_t B,
-                                                           unsigned w_lo, xyzz_t* rc) {
-    __shared__ xyzz_t sm_tree[ROWCOL_THREADS / 32];
-    __shared__ uint32_t s_start[ROWCOL_MAX_ROWS], s_pref[ROWCOL_MAX_ROWS + 1];
-    __shared__ uint32_t s_warp[ROWCOL_THREADS / 32];
-    const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
-    const unsigned g = blockIdx.z, tid = threadIdx.x, qd = tid >> 2, nq = blockDim.x >> 2;
-    const uint32_t gb0 = g * B;
-    const GiantList gl = giant_list(meta, giants);
     xyzz_t acc = xyzz_identity();
-    if (blockIdx.x < nrows) {
-        const uint32_t hi = blockIdx.x;
-        const uint32_t i_first = max(hi * W, 1u), i_last = min(hi * W + W - 1, B);
-        const uint32_t s0 = slot_of(task_off, gb0 + i_first - 1, gl), s1 = slot_of(task_off, gb0 + i_last, gl);
-        // software pipeline: the next partial is in flight while the current one is added
-        xyzz_t cur = s0 + qd < s1 ? load_xyzz(partials + s0 + qd) : xyzz_identity();
-        for (uint32_t s = s0; s < s1; s += nq) {
-            const uint32_t nx = s + nq + qd;
-            xyzz_t nxt = nx < s1 ? load_xyzz(partials + nx) : xyzz_identity();
-            acc = xyzz_add_quad<F>(acc, cur);
-            cur = nxt;
-        }
-    } else {
-        const uint32_t lo = blockIdx.x - nrows;
-        // slot range of every bucket of the column, then an exclusive scan of the range lengths (nrows <= 3 * blockDim.x)
-        uint32_t cnt[3], mysum = 0;
-#pragma unroll
-        for (unsigned k = 0; k < 3; k++) {
-            const uint32_t hi = tid * 3 + k;
-            cnt[k] = 0;
-            if (hi < nrows) {
-                const uint32_t i = hi * W + lo;
-                uint32_t st = 0;
-                if (i >= 1 && i <= B) {
-                    st = slot_of(task_off, gb0 + i - 1, gl);
-                    cnt[k] = slot_of(task_off, gb0 + i, gl) - st;
-                }
-                s_start[hi] = st;
-            }
-            mysum += cnt[k];
-        }
-        uint32_t x = mysum;
-        const unsigned lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= (unsigned)d) x += y;
-        }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        uint32_t wbase = 0;
-        for (unsigned k = 0; k < wid; k++) wbase += s_warp[k];
-        uint32_t ex = wbase + x - mysum;
-#pragma unroll
-        for (unsigned k = 0; k < 3; k++) {
-            const uint32_t hi = tid * 3 + k;
-            if (hi < nrows) s_pref[hi] = ex;
-            ex += cnt[k];
-        }
-        if (tid == blockDim.x - 1) s_pref[nrows] = ex;
-        __syncthreads();
-        const uint32_t total = s_pref[nrows];
-        auto fetch = [&](uint32_t f) -> xyzz_t {
-            if (f >= total) return xyzz_identity();
-            uint32_t l = 0, h = nrows;      // s_pref[l] <= f < s_pref[h]
-            while (h - l > 1) {
-                const uint32_t m = (l + h) >> 1;
-                if (s_pref[m] <= f) l = m; else h = m;
-            }
-            return load_xyzz(partials + s_start[l] + (f - s_pref[l]));
-        };
-        xyzz_t cur = fetch(qd);
-        for (uint32_t f0 = 0; f0 < total; f0 += nq) {
-            xyzz_t nxt = fetch(f0 + nq + qd);
-            acc = xyzz_add_quad<F>(acc, cur);
-            cur = nxt;
-        }
+    for (uint32_t j0 = j_lo; j0 < j_hi; j0 += nq) {
+        xyzz_t o = j0 + qd < j_hi ? load_xyzz(partials + t0 + j0 + qd) : xyzz_identity();
+        acc = xyzz_add_quad<F>(acc, o);
     }
-    acc = block_sum_quads<F>(acc, sm_tree);
-    if (tid == 0) store_xyzz(rc + (size_t)g * (nrows + W) + blockIdx.x, acc);
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
+    xyzz_t* mine = slice_sums + (size_t)blockIdx.x * GIANT_SLICES;
+    if (threadIdx.x == 0) {
+        store_xyzz(mine + blockIdx.y, acc);
+        __threadfence();
+        ticket_s = atomicAdd(&tickets[blockIdx.x], 1u);
+    }
+    __syncthreads();
+    if (ticket_s != GIANT_SLICES - 1) return;
+    __threadfence();
+    acc = qd < GIANT_SLICES ? load_xyzz(mine + qd) : xyzz_identity();
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
+    if (threadIdx.x == 0) { store_xyzz(buckets + b, acc); tickets[blockIdx.x] = 0; }
 }
 
-// One CTA per output bit and group: T_t = sum of C[lo] over bit t of lo (t < w_lo), of R[hi] over bit t - w_lo of hi (t >= w_lo).
-// c points per group; the group's value is sum_t 2^t T_t (finished on the host: c doublings).
+// Two-level form of the same reduction (fewer additions, shorter dependency chains).  Split i = hi * W + lo, W = 2^w_lo:
+//     sum_i i * B[i] = W * sum_hi hi * R[hi] + sum_lo lo * C[lo],   R[hi] = sum_lo B[hi W + lo],  C[lo] = sum_hi B[hi W + lo]
+// k_gridsum: one CTA per row and per column of the (B/W + 1) x W bucket grid (row B/W holds the single bucket i = B);
+// k_gridsum_final: one CTA per output bit: T_t = sum of C[lo] over bit t of lo (t < w_lo), of R[hi] over bit t - w_lo of hi
+// (t >= w_lo).  Output layout and meaning are those of k_bitsum_final: c points per group, the MSM is sum_t 2^t T_t.
+// About 2 B additions per group instead of (c - 1) B / 2.
 template <class F>
-__global__ void __launch_bounds__(TREE_THREADS) k_bit_slices(const xyzz_t* __restrict__ rc, uint32_t B, unsigned w_lo, unsigned c, xyzz_t* out) {
-    __shared__ xyzz_t sm_tree[TREE_THREADS / 32];
+__global__ void __launch_bounds__(TREE_THREADS) k_gridsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned w_lo, xyzz_t* rc) {
+    extern __shared__ xyzz_t sm_tree[];
+    const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
+    const unsigned g = blockIdx.z;
+    const xyzz_t* bk = buckets + (size_t)g * B;
+    const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
+    const bool row = blockIdx.x < nrows;
+    const uint32_t fixed = row ? blockIdx.x : blockIdx.x - nrows, count = row ? W : nrows;
+    xyzz_t acc = xyzz_identity();
+    for (uint32_t e0 = 0; e0 < count; e0 += nq) {
+        const uint32_t e = e0 + qd;
+        xyzz_t o = xyzz_identity();
+        if (e < count) {
+            const uint32_t i = row ? fixed * W + e : e * W + fixed;
+            if (i >= 1 && i <= B) o = load_xyzz(bk + (i - 1));
+        }
+        acc = xyzz_add_quad<F>(acc, o);
+    }
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
+    if (threadIdx.x == 0) store_xyzz(rc + (size_t)g * (nrows + W) + blockIdx.x, acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(TREE_THREADS) k_gridsum_final(const xyzz_t* __restrict__ rc, uint32_t B, unsigned w_lo, unsigned c, xyzz_t* out) {
+    extern __shared__ xyzz_t sm_tree[];
     const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
     const unsigned t = blockIdx.x, g = blockIdx.y;
     const bool cols = t < w_lo;
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(TREE_THREADS) k_bit_slices(const xyzz_t* __res
         xyzz_t o = e < count ? load_xyzz(src + e) : xyzz_identity();
         acc = xyzz_add_quad<F>(acc, o);
     }
-    acc = block_sum_quads<F>(acc, sm_tree);
+    acc = block_tree_sum_quad<F>(acc, sm_tree);
     if (threadIdx.x == 0) store_xyzz(out + (size_t)g * c + t, acc);
 }
 
@@ -484,11 +484,17 @@ static void free_dev(void* p) { if (p) cudaFree(p); }
 
 void msm_workspace_free(MsmWorkspace& ws) {
     free_dev(ws.d_digits); free_dev(ws.d_entries); free_dev(ws.d_partials);
-    free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_chain); free_dev(ws.d_chain_flag);
+    free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_buckets); free_dev(ws.d_chain); free_dev(ws.d_chain_flag);
     free_dev(ws.d_bitsums); free_dev(ws.d_meta); free_dev(ws.d_giants); free_dev(ws.d_giant_slices); free_dev(ws.d_giant_tickets);
     if (ws.h_bitsums) cudaFreeHost(ws.h_bitsums);
     for (auto& e : ws.ev) if (e) cudaEventDestroy(e);
     ws = MsmWorkspace();
+}
+
+static unsigned pow2_ceil_log(uint64_t x) {
+    unsigned l = 0;
+    while (((uint64_t)1 << l) < x) l++;
+    return l;
 }
 
 template <class F, class FS>
@@ -515,30 +521,39 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
         zk_set_error("msm: %zu x %u x %u entries exceed the 31-bit index space", n, nwin, k);
         return ZK_ERR_INVALID;
     }
-    // Entries per accumulation task: the tasks fill the machine ONCE (wave_threads accumulation threads per SM; the mixed
-    // addition rate saturates from ~8 warps per SM, tools/microbench.py) — every further task is one more partial for the
-    // latency-bound reduction behind the accumulation.  Very large inputs get several waves of <= 256-entry tasks.
-    const size_t wave_threads = ws.wave_threads ? ws.wave_threads : 384;
-    const size_t capacity = (size_t)ws.sm_count * wave_threads;
+    // Entries per accumulation task: the accumulate kernel keeps `capacity` threads resident (4 CTAs of 128 per SM at
+    // <= 128 registers); K is chosen so that the tasks fill a whole number of waves (a 1.02-wave grid costs two waves).
+    // Short tasks keep the lanes of a warp balanced (a bucket of n_b entries is cut into ceil(n_b / K) equal parts: lengths lie
+    // in (K s / (s + 1), K]) — measured on B200: one 28-entry wave is 1.5x slower than two 8-entry waves for the same additions.
+    const size_t capacity = (size_t)ws.sm_count * (ws.wave_threads ? ws.wave_threads : 512);
+    const size_t resident_quads = (size_t)ws.sm_count * TREE_QUADS;
+    const bool many_buckets = NB > resident_quads;    // many small buckets: throughput regime (see k_bucket_finish_serial)
+    const bool serial_finish = many_buckets;
     uint32_t K = ws.chunk;
     if (K == 0) {
         const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
-        size_t waves = (Mmax + 256 * capacity - 1) / (256 * capacity);
+        size_t waves = (Mmax + 64 * capacity - 1) / (64 * capacity);   // long tasks for large inputs: fewer partials to sum
         if (waves == 0) waves = 1;
+        // a cheap finish pass affords twice as many (half as long, better balanced) tasks
+        if (many_buckets && Mmax / (2 * waves * capacity) >= 6) waves *= 2;
         K = (uint32_t)((Mmax + waves * capacity - slack - 1) / (waves * capacity - slack));
         if (K < 4) K = 4;
     }
     const size_t NTmax = Mmax / K + NB + 1;           // sum_b ceil(n_b / K) <= M / K + (number of non-empty buckets)
-    const uint32_t smax = 8 * (ROWCOL_THREADS / 4);   // more partials than this in one bucket: "giant" (side area + k_giant_finish)
+    // lanes per bucket in the finish pass: ~a quarter of the expected partials per bucket
+    const uint64_t s_avg = Mmax / ((uint64_t)K * NB) + 1;
+    unsigned log_g = pow2_ceil_log((s_avg + 7) / 8);   // quads per bucket in the finish pass
+    if (log_g > 3) log_g = 3;
+    const uint32_t smax = 32u << log_g;               // more partials than this: the bucket is "giant"
+    const uint32_t run = 4;                           // k_run_sum: consecutive partials summed per thread
     const unsigned w_lo = (c - 1) / 2;
     const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
     const size_t ntiles = (NB + PLAN_TILE - 1) / PLAN_TILE;
 
     static_assert(sizeof(xyzz_t) == 128 && sizeof(affine_t) == 64 && sizeof(fe) == 32, "layout");
-    if (nrows > ROWCOL_MAX_ROWS || nrows > 3 * ROWCOL_THREADS) { zk_set_error("msm: window %u has too many bucket rows", c); return ZK_ERR_INVALID; }
-    // scratch, grouped by what sizes it: the entry list (k * n * nwin), the bucket counters (G * B), the slice sums (G * c)
+    // scratch, grouped by what sizes it: the entry list (k * n * nwin), the bucket array (G * B), the slice sums (G * c)
     {
-        const size_t need_entries = Mmax * sizeof(uint32_t), need_partials = (NTmax + MSM_MAX_GIANTS) * sizeof(xyzz_t);
+        const size_t need_entries = Mmax * sizeof(uint32_t), need_partials = NTmax * sizeof(xyzz_t);
         if (ws.cap_entries < need_entries) {
             free_dev(ws.d_digits); free_dev(ws.d_entries);
             ws.d_digits = nullptr; ws.d_entries = nullptr; ws.cap_entries = 0;
@@ -553,11 +568,12 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
             ws.cap_partials = need_partials;
         }
         if (ws.cap_buckets < NB) {
-            free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_chain); free_dev(ws.d_chain_flag);
-            ws.d_counts = ws.d_offsets = ws.d_task_off = ws.d_chain_flag = nullptr; ws.d_chain = nullptr; ws.cap_buckets = 0;
+            free_dev(ws.d_counts); free_dev(ws.d_offsets); free_dev(ws.d_task_off); free_dev(ws.d_buckets); free_dev(ws.d_chain); free_dev(ws.d_chain_flag);
+            ws.d_counts = ws.d_offsets = ws.d_task_off = ws.d_chain_flag = nullptr; ws.d_chain = nullptr; ws.d_buckets = nullptr; ws.cap_buckets = 0;
             ZK_CUDA(cudaMalloc(&ws.d_counts, NB * sizeof(uint32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_offsets, (NB + 1) * sizeof(uint32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_task_off, (NB + 1) * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_buckets, NB * sizeof(xyzz_t)));
             ZK_CUDA(cudaMalloc(&ws.d_chain, ntiles * sizeof(uint64_t)));
             ZK_CUDA(cudaMalloc(&ws.d_chain_flag, ntiles * sizeof(uint32_t)));
             ZK_CUDA(cudaMemsetAsync(ws.d_chain_flag, 0, ntiles * sizeof(uint32_t), st));
@@ -580,7 +596,7 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
         }
         if (!ws.d_meta) {
             ZK_CUDA(cudaMalloc(&ws.d_meta, 8 * sizeof(uint32_t)));
-            ZK_CUDA(cudaMalloc(&ws.d_giants, 3 * MSM_MAX_GIANTS * sizeof(uint32_t)));
+            ZK_CUDA(cudaMalloc(&ws.d_giants, MSM_MAX_GIANTS * sizeof(uint32_t)));
             ZK_CUDA(cudaMalloc(&ws.d_giant_slices, (size_t)MSM_MAX_GIANTS * GIANT_SLICES * sizeof(xyzz_t)));
             ZK_CUDA(cudaMalloc(&ws.d_giant_tickets, MSM_MAX_GIANTS * sizeof(uint32_t)));
             ZK_CUDA(cudaMemsetAsync(ws.d_giant_tickets, 0, MSM_MAX_GIANTS * sizeof(uint32_t), st));
@@ -595,12 +611,13 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
     for (unsigned j = 0; j < k; j++) sc.p[j] = d_scalars[j];
     const uint32_t epoch = ++ws.epoch;
     ZK_CUDA(cudaMemsetAsync(ws.d_counts, 0, NB * sizeof(uint32_t), st));
+    ZK_CUDA(cudaMemsetAsync(ws.d_buckets, 0, NB * sizeof(xyzz_t), st));  // all-zero XYZZ == identity
     STAGE_MARK(0);
     // 1. digits + histogram
     k_recode<FS><<<dim3((unsigned)((n + 127) / 128), k), 128, 0, st>>>(sc, scalars_mont ? 1 : 0, n, c, nwin, gpm, use_table ? 0 : 1, ws.d_digits,
                                                                         ws.d_counts, ws.d_meta);
     STAGE_MARK(1);
-    // 2. plan: bucket offsets, task offsets, giant list and side areas
+    // 2. plan: bucket offsets, task offsets, giant list
     k_plan<<<(unsigned)ntiles, 1024, 0, st>>>(ws.d_counts, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, ws.d_giants, ws.d_chain,
                                                ws.d_chain_flag, epoch);
     STAGE_MARK(2);
@@ -610,20 +627,36 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
     STAGE_MARK(3);
     // 4. accumulation: one task per <= K sorted entries of one bucket
     k_accumulate<F><<<(unsigned)((NTmax + 127) / 128), 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, ws.d_meta,
-                                                                   ws.d_giants, d_extra, (uint32_t)main_count, ws.d_partials);
+                                                                   d_extra, (uint32_t)main_count, ws.d_buckets, ws.d_partials);
     STAGE_MARK(4);
-    // 5. giants to one slot each, then row / column sums straight from the partial list
-    k_giant_finish<F><<<dim3(GIANT_GRID, GIANT_SLICES), TREE_THREADS, 0, st>>>(ws.d_giants, ws.d_meta, ws.d_task_off, ws.d_partials, ws.d_giant_slices,
-                                                                                 ws.d_giant_tickets);
+    // 5. per-bucket sums of the task partials (+ giants)
+    // giants first: k_giant_finish reads the untouched partial lists, k_run_sum then rewrites partials in place
+    k_giant_finish<F><<<dim3(64, GIANT_SLICES), TREE_THREADS, TREE_QUADS * sizeof(xyzz_t), st>>>(
+        ws.d_giants, ws.d_meta, ws.d_offsets, ws.d_task_off, K, ws.d_buckets, ws.d_partials, ws.d_giant_slices, ws.d_giant_tickets);
+    if (serial_finish) {
+        const size_t threads = (NTmax + run - 1) / run;
+        k_run_sum<F><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ws.d_task_off, (uint32_t)NB, ws.d_meta, run, smax, ws.d_partials);
+        nl += 1;
+        k_bucket_finish_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, ws.d_meta, run, ws.d_buckets, ws.d_partials);
+    } else {
+        k_bucket_finish<F><<<(unsigned)(((NB << (log_g + 2)) + 127) / 128), 128, 0, st>>>(ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, smax, log_g, ws.d_meta,
+                                                                                  ws.d_buckets, ws.d_partials);
+    }
+    STAGE_MARK(5);
+    // 6. two-level bucket reduction: row / column sums of the bucket grid, then their bit slices
     xyzz_t* d_rc = ws.d_bitsums;
     xyzz_t* d_T = ws.d_bitsums + (size_t)G * (nrows + W);
-    k_rowcol<F><<<dim3(nrows + W, 1, G), ROWCOL_THREADS, 0, st>>>(ws.d_partials, ws.d_task_off, ws.d_meta, ws.d_giants, B, w_lo, d_rc);
-    STAGE_MARK(5);
-    // 6. bit slices of the row / column sums
-    unsigned ft = TREE_THREADS;                 // half of the elements carry a given bit
-    while (ft > 32 && ft / 4 >= std::max(W, nrows)) ft /= 2;
-    k_bit_slices<F><<<dim3(c, G), ft, 0, st>>>(d_rc, B, w_lo, c, d_T);
-    nl += 7;
+    {
+        // a quad per 1-2 elements of a row / column, but never more CTAs x threads than are resident at once (the kernels
+        // need ~190 registers: 320 threads per SM), so that the whole grid runs as one wave
+        unsigned gt = TREE_THREADS;
+        while (gt > 32 && (gt / 4 >= 2 * std::max(W, nrows) || (size_t)G * (nrows + W) * gt > (size_t)ws.sm_count * 320)) gt /= 2;
+        k_gridsum<F><<<dim3(nrows + W, 1, G), gt, (gt / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, w_lo, d_rc);
+        unsigned ft = TREE_THREADS;                 // half of the elements carry a given bit
+        while (ft > 32 && ft / 4 >= std::max(W, nrows)) ft /= 2;
+        k_gridsum_final<F><<<dim3(c, G), ft, (ft / 4) * sizeof(xyzz_t), st>>>(d_rc, B, w_lo, c, d_T);
+    }
+    nl += 8;
     STAGE_MARK(6);
     ZK_CUDA(cudaGetLastError());
     shape->c = c; shape->groups = gpm;

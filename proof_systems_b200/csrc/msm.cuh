@@ -14,14 +14,14 @@
 //   * scalars are recoded to signed base-2^c digits in (-2^(c-1), 2^(c-1)]; (digit != 0) entries are counting-sorted by
 //     bucket (histogram -> scan -> scatter, all on device);
 //   * accumulation is task based: the histogram is known before any point is touched, so every bucket's sorted entries
-//     are cut into ceil(n_b / K) nearly equal tasks; a thread sums one task (<= K XYZZ mixed additions) and leaves one
-//     partial sum per task, in bucket order.  No atomics touch curve points;
-//   * bucket reduction sum_b (b+1) B_b never materialises the buckets: with b+1 = hi * W + lo the sum is
-//     W * sum_hi hi R[hi] + sum_lo lo C[lo], and the row sums R[hi] / column sums C[lo] are sums over TASK PARTIALS (a row is a
-//     contiguous range of the partial list), so one kernel goes from partials to the ~2 sqrt(B) row/column sums; a second one
-//     bit-slices those (T_t = sum of the rows / columns whose index has bit t set) and the host finishes with c doublings.
-//     The rare giant bucket (all points in one bucket: the kimchi witness columns) keeps its partials in a side
-//     area that 16 CTAs reduce to one slot first;
+//     are cut into ceil(n_b / K) nearly equal tasks; a thread sums one task (<= K XYZZ mixed additions).  The task partials of
+//     a bucket are summed thread-parallel in two balanced levels (runs of 4 consecutive partials, then <= 4 run sums per
+//     bucket) — thread-serial additions have twice the throughput of the quad-cooperative ones (tools/microbench.py), so the
+//     bulk of the reduction stays thread-serial and quads are kept for the short dependent tails.  The rare giant bucket (all
+//     points in one bucket — the kimchi witness columns) gets 16 CTAs.  No atomics touch curve points;
+//   * bucket reduction sum_b (b+1) B_b in two levels: with b+1 = hi * W + lo the sum is W * sum_hi hi R[hi] + sum_lo lo C[lo]
+//     (row / column sums of the bucket grid, one CTA each), then bit slices T_t = sum of the rows / columns whose index has
+//     bit t set, and the host finishes with c doublings;
 //   * k MSMs over the same bases (the chunks of t, the 15 witness columns, the L/R pair of an IPA round) run as ONE pipeline
 //     with k bucket groups: every latency-bound stage is paid once per batch, not once per MSM.
 #pragma once
@@ -32,7 +32,7 @@
 namespace zkb {
 
 constexpr unsigned MSM_MAX_WINDOW_BITS = 16;
-constexpr uint32_t MSM_MAX_GIANTS = 256;      // buckets with > smax tasks keep their partials in a side area (k_giant_finish)
+constexpr uint32_t MSM_MAX_GIANTS = 64;       // buckets with > smax tasks get 16 CTAs each (k_giant_finish)
 constexpr unsigned MSM_MAX_BATCH = 16;        // MSMs fused into one pipeline (scalar pointers travel as a kernel parameter)
 struct MsmScalarSet {
     const fe* p[MSM_MAX_BATCH];
@@ -52,10 +52,11 @@ struct MsmWorkspace {
     size_t cap_entries = 0, cap_partials = 0, cap_buckets = 0, cap_bits = 0, cap_hbits = 0;
     int32_t* d_digits = nullptr;      // [k][nwin][n]
     uint32_t* d_entries = nullptr;    // [M]  point index | sign << 31, sorted by bucket
-    xyzz_t* d_partials = nullptr;     // [tasks + giants] one partial sum per accumulation task (main slots, then giant areas)
+    xyzz_t* d_partials = nullptr;     // [tasks] one partial sum per accumulation task
     uint32_t* d_counts = nullptr;     // [NB]     histogram, then scatter cursors
     uint32_t* d_offsets = nullptr;    // [NB + 1] exclusive scan of the counts
     uint32_t* d_task_off = nullptr;   // [NB + 1] exclusive scan of ceil(count / K)
+    xyzz_t* d_buckets = nullptr;      // [NB]
     uint64_t* d_chain = nullptr;      // [tiles] chained scan of k_plan: inclusive (entries << 32 | tasks) per tile
     uint32_t* d_chain_flag = nullptr; // [tiles] epoch stamps of d_chain
     uint32_t epoch = 0;               // bumped per run (no flag memset)
@@ -65,8 +66,8 @@ struct MsmWorkspace {
     xyzz_t* d_T_out = nullptr;        // when set: the slice sums are copied HERE (device, capacity d_T_cap points) instead of to
     size_t d_T_cap = 0;               // the host, and nothing is synchronised (multi-GPU exchange, zk_msm_partial)
     bool defer_sync = false;          // msm_run returns after enqueueing the D2H copy; the caller synchronises
-    uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets, [3] main slots, [4] plan tiles done
-    uint32_t* d_giants = nullptr;     // [3][MSM_MAX_GIANTS]: bucket ids | task counts | first slot of the side area
+    uint32_t* d_meta = nullptr;       // [0] sorted entries, [1] tasks, [2] giant buckets
+    uint32_t* d_giants = nullptr;     // [MSM_MAX_GIANTS] bucket ids
     xyzz_t* d_giant_slices = nullptr; // [MSM_MAX_GIANTS][GIANT_SLICES] per-CTA slice sums of a giant's partials
     uint32_t* d_giant_tickets = nullptr;  // [MSM_MAX_GIANTS] arrival counters (self-resetting)
     uint32_t chunk = 0;               // K override (0: chosen per call so that the tasks fill the machine once)

@@ -279,3 +279,24 @@ def test_partial_and_finish_gathered_emulate_two_ranks(ctx, orc, vesta_srs):
         with pytest.raises(zk.ZkError):
             ctx.msm_partial(bases, d_sc.data_ptr(), n, d_all.data_ptr(), 1)      # buffer too small for the slice sums
         bases.free()
+
+
+def test_synthetic_points_are_on_the_curve_and_deterministic(ctx, orc):
+    """zk_points_synthetic (inputs of BASELINE config 4 in bench.py): every point satisfies y^2 = x^3 + 5, the sequence depends only
+    on (curve, seed, index), and an MSM over them agrees with the oracle."""
+    for cid in (zk.PALLAS, zk.VESTA):
+        fid = orc.BASE_FIELD[cid]
+        p = ctx.synthetic_points(cid, 3000, seed=9)
+        assert np.array_equal(p, ctx.synthetic_points(cid, 3000, seed=9))
+        assert np.array_equal(p[:1000], ctx.synthetic_points(cid, 1000, seed=9))
+        assert not np.array_equal(p[:8], ctx.synthetic_points(cid, 8, seed=10))
+        x, y = np.ascontiguousarray(p[:, :4]), np.ascontiguousarray(p[:, 4:])
+        five = orc.to_mont(fid, orc.ints_to_limbs([5] * len(p)))
+        lhs = ctx.field_op(fid, "mul", y, y)
+        rhs = ctx.field_op(fid, "add", ctx.field_op(fid, "mul", ctx.field_op(fid, "mul", x, x), x), five)
+        assert np.array_equal(lhs, rhs)
+        assert len({bytes(r) for r in x}) == len(p)                      # distinct points
+        sc = orc.random_scalars(orc.SCALAR_FIELD[cid], len(p), seed=11)
+        b = ctx.upload_bases(cid, p, window_bits=-1)
+        assert np.array_equal(ctx.msm_affine(b, sc), orc.msm(cid, p, sc))
+        b.free()

@@ -10,7 +10,7 @@ for spec in "$@"; do
   dir=/tmp/zkb_build_$tag; mkdir -p $dir
   for f in api msm ntt srs group_ntt decompress ipa open $EXTRA_SRCS; do
     [ -f $f.cu ] || continue
-    $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -ccbin /usr/bin/g++ \
+    $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -ccbin /usr/bin/g++ \
       --expt-relaxed-constexpr $flags -c -o $dir/$f.o $f.cu &
   done
   wait
