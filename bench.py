@@ -417,8 +417,10 @@ def main():
         for _ in range(3):
             roundtrip()
         rt_ms = max_over_ranks(timed(roundtrip, args.steps)) / args.steps
+        stream.synchronize()
         rt_exact = bool(torch.equal(d3, d3_0))
         ctx.ntt_dev(zk.FP, d3.data_ptr(), L3)
+        stream.synchronize()                      # the library runs on `stream`; torch's copy below does not
         fwd3 = d3.cpu().numpy().view(np.uint64).reshape(n3, 4)
         d3.copy_(d3_0)
         k3 = ntt_profile(lambda: ctx.ntt_dev(zk.FP, d3.data_ptr(), L3), 5)

@@ -140,6 +140,20 @@ int zk_ntt_batch(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, size
                  int coset);
 int zk_ntt_dev(zk_ctx* ctx, int field_id, void* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse,
                int coset);
+/* Out of place, device to device: polynomial b is read from d_in + b * in_stride elements (its first in_len elements, the rest
+ * of the domain is taken as zero) and its transform written to d_out + b * 2^log_n — DensePolynomial::evaluate_over_domain_by_ref
+ * of n coefficients over d8 (kimchi/src/circuits/constraints.rs:488-507) without materialising the zero padding, and the
+ * building block of a device-resident iFFT(n) -> FFT(8n) -> pointwise -> iFFT(8n) pipeline.
+ * log_n up to 30 (three passes beyond 2^20). */
+int zk_ntt_dev_oop(zk_ctx* ctx, int field_id, const void* d_in, size_t in_stride, size_t in_len, void* d_out, unsigned log_n,
+                   size_t batch, int inverse, int coset);
+
+/* Device memory for callers without a CUDA binding of their own (the Rust shim keeps witness / quotient polynomials resident
+ * between calls of the *_dev entry points).  Synchronous copies; pointers are plain device pointers. */
+int zk_dev_alloc(zk_ctx* ctx, size_t bytes, void** out);
+int zk_dev_free(zk_ctx* ctx, void* d_ptr);
+int zk_dev_upload(zk_ctx* ctx, void* d_dst, const void* src, size_t bytes);
+int zk_dev_download(zk_ctx* ctx, void* dst, const void* d_src, size_t bytes);
 
 /* ------------------------------------------------------------------ SRS mirror (poly-commitment/src/lib.rs:61-241, ipa.rs)
  * zk_srs_create            SRS{g, h} with g resident on the device            (ipa.rs:56-75)

@@ -100,6 +100,11 @@ def lib() -> ctypes.CDLL:
     if os.environ.get("ZKB200_LIB") and not hasattr(L, "zk_points_synthetic"):
         return L      # an A/B build of an older tree (tools/build_variants.sh): the newest entry points are absent
     L.zk_points_synthetic.argtypes = [vp, i, ctypes.c_uint64, sz, vp]
+    L.zk_ntt_dev_oop.argtypes = [vp, i, vp, sz, sz, vp, u, sz, i, i]
+    L.zk_dev_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+    L.zk_dev_free.argtypes = [vp, vp]
+    L.zk_dev_upload.argtypes = [vp, vp, vp, sz]
+    L.zk_dev_download.argtypes = [vp, vp, vp, sz]
     L.zk_srs_open.argtypes = [vp, ctypes.POINTER(OpenPoly), sz, vp, sz, vp, vp, vp, sz, ctypes.POINTER(OpenTranscript), vp, sz,
                               ctypes.POINTER(sz), vp, vp, vp, vp]
     return L
@@ -289,6 +294,29 @@ class Context:
 
     def ntt_dev(self, field: int, d_data: int, log_n: int, batch: int = 1, in_len: int = 0, inverse: bool = False, coset: bool = False):
         check(lib().zk_ntt_dev(self._h, field, ctypes.c_void_p(d_data), log_n, batch, in_len, int(inverse), int(coset)))
+
+    def ntt_dev_oop(self, field: int, d_in: int, in_stride: int, in_len: int, d_out: int, log_n: int, batch: int = 1, inverse: bool = False,
+                    coset: bool = False):
+        """out of place, device to device: polynomial b read from d_in + b * in_stride (first in_len elements), written to d_out + b * 2^log_n"""
+        check(lib().zk_ntt_dev_oop(self._h, field, ctypes.c_void_p(d_in), in_stride, in_len, ctypes.c_void_p(d_out), log_n, batch, int(inverse), int(coset)))
+
+    # ------------------------------------------------------------------ device memory (zk_dev_*)
+    def dev_alloc(self, nbytes: int) -> int:
+        p = ctypes.c_void_p()
+        check(lib().zk_dev_alloc(self._h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def dev_free(self, d_ptr: int):
+        check(lib().zk_dev_free(self._h, ctypes.c_void_p(d_ptr)))
+
+    def dev_upload(self, d_dst: int, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        check(lib().zk_dev_upload(self._h, ctypes.c_void_p(d_dst), _ptr(a), a.nbytes))
+
+    def dev_download(self, d_src: int, shape, dtype=np.uint64) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        check(lib().zk_dev_download(self._h, _ptr(out), ctypes.c_void_p(d_src), out.nbytes))
+        return out
 
     # ------------------------------------------------------------------ diagnostics
     def field_op(self, field: int, op: str, a, b=None) -> np.ndarray:

@@ -119,7 +119,7 @@ static int ctx_ntt_tables(zk_ctx* ctx, int field, unsigned log_n, bool inverse, 
         NttTables t;
         int rc = field == ZK_FP ? ntt_build_tables<FpParams>(t, log_n, inverse, ctx->stream) : ntt_build_tables<FqParams>(t, log_n, inverse, ctx->stream);
         if (rc) return rc;
-        ctx->launches += 5;
+        ctx->launches += t.full ? 8 : 7;
         it = ctx->ntt_tables.emplace(key, t).first;
     }
     *small = sm;
@@ -127,13 +127,21 @@ static int ctx_ntt_tables(zk_ctx* ctx, int field, unsigned log_n, bool inverse, 
     return ZK_OK;
 }
 
-int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
+// Transform of `batch` polynomials: polynomial b is read from d_in + b * in_bs (its first in_len elements) and written to
+// d_out + b * 2^log_n; d_in == d_out (in_bs = 2^log_n) is the in-place form.
+int ctx_ntt_device_oop(zk_ctx* ctx, int field, const fe* d_in, size_t in_bs, fe* d_out, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
     if (field != ZK_FP && field != ZK_FQ) { zk_set_error("ntt: unknown field_id %d", field); return ZK_ERR_INVALID; }
     if (log_n > NTT_MAX_LOG_N) { zk_set_error("ntt: log_n %u > %u not supported", log_n, NTT_MAX_LOG_N); return ZK_ERR_INVALID; }
     const fe* small;
     const NttTables* tabs;
+    const NttTables* inner = nullptr;
     int rc = ctx_ntt_tables(ctx, field, log_n, inverse != 0, &small, &tabs);
     if (rc) return rc;
+    if (const unsigned log_inner = ntt_inner_log(log_n)) {
+        const fe* small2;
+        rc = ctx_ntt_tables(ctx, field, log_inner, inverse != 0, &small2, &inner);
+        if (rc) return rc;
+    }
     size_t bytes = ((size_t)batch << log_n) * sizeof(fe);
     fe* tmp = nullptr;
     if (log_n > NTT_MAX_LOG_SUB) {
@@ -146,8 +154,8 @@ int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t ba
         if (!ctx->ev_ntt[0]) { ZK_CUDA(cudaEventCreate(&ctx->ev_ntt[0])); ZK_CUDA(cudaEventCreate(&ctx->ev_ntt[1])); }
         ZK_CUDA(cudaEventRecord(ctx->ev_ntt[0], ctx->stream));
     }
-    rc = field == ZK_FP ? ntt_run<FpParams>(d_data, tmp, small, *tabs, log_n, batch, in_len, inverse != 0, coset != 0, ctx->stream, &nl)
-                        : ntt_run<FqParams>(d_data, tmp, small, *tabs, log_n, batch, in_len, inverse != 0, coset != 0, ctx->stream, &nl);
+    rc = field == ZK_FP ? ntt_run<FpParams>(d_in, in_bs, d_out, tmp, small, *tabs, inner, log_n, batch, in_len, inverse != 0, coset != 0, ctx->stream, &nl)
+                        : ntt_run<FqParams>(d_in, in_bs, d_out, tmp, small, *tabs, inner, log_n, batch, in_len, inverse != 0, coset != 0, ctx->stream, &nl);
     ctx->launches += nl;
     if (rc == ZK_OK && ctx->profile) {
         ZK_CUDA(cudaEventRecord(ctx->ev_ntt[1], ctx->stream));
@@ -155,6 +163,10 @@ int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t ba
         ZK_CUDA(cudaEventElapsedTime(&ctx->ntt_ms, ctx->ev_ntt[0], ctx->ev_ntt[1]));
     }
     return rc;
+}
+
+int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
+    return ctx_ntt_device_oop(ctx, field, d_data, (size_t)1 << (log_n > 62 ? 0 : log_n), d_data, log_n, batch, in_len, inverse, coset);
 }
 
 // ---------------------------------------------------------------------------------------------- diagnostics kernels
@@ -574,6 +586,53 @@ int zk_ntt_dev(zk_ctx* ctx, int field_id, void* d_data, unsigned log_n, size_t b
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));
     return ctx_ntt_device(ctx, field_id, (fe*)d_data, log_n, batch, in_len, inverse, coset);
+}
+
+int zk_ntt_dev_oop(zk_ctx* ctx, int field_id, const void* d_in, size_t in_stride, size_t in_len, void* d_out, unsigned log_n, size_t batch, int inverse,
+                   int coset) {
+    if (!ctx || ((!d_in || !d_out) && batch)) { zk_set_error("ntt: null argument"); return ZK_ERR_INVALID; }
+    if (log_n > NTT_MAX_LOG_N) { zk_set_error("ntt: log_n %u > %u not supported", log_n, NTT_MAX_LOG_N); return ZK_ERR_INVALID; }
+    const size_t n = (size_t)1 << log_n;
+    if (in_len == 0 || in_len > n) in_len = n;
+    if (in_stride < in_len && batch > 1) { zk_set_error("ntt: input stride %zu shorter than the %zu elements read per polynomial", in_stride, in_len); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    return ctx_ntt_device_oop(ctx, field_id, (const fe*)d_in, in_stride, (fe*)d_out, log_n, batch, in_len, inverse, coset);
+}
+
+// ---------------------------------------------------------------------------------------------- device memory for the *_dev entry points
+int zk_dev_alloc(zk_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) { zk_set_error("dev_alloc: null argument"); return ZK_ERR_INVALID; }
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return ZK_OK;
+}
+int zk_dev_free(zk_ctx* ctx, void* d_ptr) {
+    if (!ctx) { zk_set_error("dev_free: null argument"); return ZK_ERR_INVALID; }
+    if (!d_ptr) return ZK_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(cudaFree(d_ptr));
+    return ZK_OK;
+}
+int zk_dev_upload(zk_ctx* ctx, void* d_dst, const void* src, size_t bytes) {
+    if (!ctx || ((!d_dst || !src) && bytes)) { zk_set_error("dev_upload: null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));   // the source may be pageable and reused by the caller
+    return ZK_OK;
+}
+int zk_dev_download(zk_ctx* ctx, void* dst, const void* d_src, size_t bytes) {
+    if (!ctx || ((!dst || !d_src) && bytes)) { zk_set_error("dev_download: null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
 }
 
 int zk_ntt_batch(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {

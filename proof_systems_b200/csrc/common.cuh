@@ -69,6 +69,12 @@ __device__ __forceinline__ fe shfl_fe(const fe& a, int src_lane) {
     for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src_lane);
     return r;
 }
+__device__ __forceinline__ fe shfl_xor_fe(const fe& a, int m) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], m);
+    return r;
+}
 __device__ __forceinline__ fe shfl_up_fe(const fe& a, unsigned d) {
     fe r;
 #pragma unroll

@@ -47,6 +47,7 @@ int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, con
 int ctx_ensure(void** p, size_t* cap, size_t bytes);
 // the NTT of zk_ntt_dev without the context lock (the caller holds it)
 int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset);
+int ctx_ntt_device_oop(zk_ctx* ctx, int field, const fe* d_in, size_t in_bs, fe* d_out, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset);
 // k independent MSMs over the same bases slice [off, off + n), scalars j at d_scalars[j] (device memory, ordered after
 // ctx->stream), fused into pipelines of up to ctx->batch MSMs (msm.cuh).  Results (Jacobian) to out_xyz + 12 j.
 // d_extra / n_extra: points of this call only, laid out like the table (msm.cuh); every scalar vector then has n + n_extra entries.

@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(TREE_THREADS) k_giant_finish(const uint32_t* _
 // (t >= w_lo).  Output layout and meaning are those of k_bitsum_final: c points per group, the MSM is sum_t 2^t T_t.
 // About 2 B additions per group instead of (c - 1) B / 2.
 template <class F>
-__global__ void __launch_bounds__(TREE_THREADS) k_gridsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned w_lo, xyzz_t* rc) {
+__global__ void __launch_bounds__(128, 3) k_gridsum(const xyzz_t* __restrict__ buckets, uint32_t B, unsigned w_lo, xyzz_t* rc) {
     extern __shared__ xyzz_t sm_tree[];
     const uint32_t W = 1u << w_lo, nrows = (B >> w_lo) + 1;
     const unsigned g = blockIdx.z;
@@ -531,13 +531,15 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
     const bool serial_finish = many_buckets;
     uint32_t K = ws.chunk;
     if (K == 0) {
+        // (1) lane balance: a bucket of n_b entries is cut into ceil(n_b / K) equal tasks, so task lengths lie in (K s / (s + 1), K];
+        //     with s >= 8 tasks per average bucket the lanes of a warp differ by ~10% (measured on B200, 2^16 points, window 15: tasks
+        //     of 28 entries run the same additions 1.5x slower than tasks of 8), whatever the batch size;
+        // (2) small inputs: never fewer tasks than threads the machine holds at once.
+        const size_t n_avg = std::max<size_t>(1, Mmax / NB);
+        size_t k_bal = many_buckets ? std::min<size_t>(64, std::max<size_t>(4, n_avg / 8)) : 64;
         const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
-        size_t waves = (Mmax + 64 * capacity - 1) / (64 * capacity);   // long tasks for large inputs: fewer partials to sum
-        if (waves == 0) waves = 1;
-        // a cheap finish pass affords twice as many (half as long, better balanced) tasks
-        if (many_buckets && Mmax / (2 * waves * capacity) >= 6) waves *= 2;
-        K = (uint32_t)((Mmax + waves * capacity - slack - 1) / (waves * capacity - slack));
-        if (K < 4) K = 4;
+        const size_t k_cap = std::max<size_t>(4, (Mmax + capacity - slack - 1) / (capacity - slack));
+        K = (uint32_t)std::min(k_bal, k_cap);
     }
     const size_t NTmax = Mmax / K + NB + 1;           // sum_b ceil(n_b / K) <= M / K + (number of non-empty buckets)
     // lanes per bucket in the finish pass: ~a quarter of the expected partials per bucket
@@ -647,10 +649,10 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
     xyzz_t* d_rc = ws.d_bitsums;
     xyzz_t* d_T = ws.d_bitsums + (size_t)G * (nrows + W);
     {
-        // a quad per 1-2 elements of a row / column, but never more CTAs x threads than are resident at once (the kernels
-        // need ~190 registers: 320 threads per SM), so that the whole grid runs as one wave
-        unsigned gt = TREE_THREADS;
-        while (gt > 32 && (gt / 4 >= 2 * std::max(W, nrows) || (size_t)G * (nrows + W) * gt > (size_t)ws.sm_count * 320)) gt /= 2;
+        // a quad per 1-4 elements of a row / column, but never more CTAs x threads than are resident at once (384 threads per
+        // SM at the kernel's register budget), so that the whole grid of a single MSM — 385 CTAs at window 16 — runs as one wave
+        unsigned gt = 128;                          // k_gridsum is built for 3 CTAs of 128 threads per SM (<= 168 registers)
+        while (gt > 32 && (gt / 4 >= 2 * std::max(W, nrows) || (size_t)G * (nrows + W) * gt > (size_t)ws.sm_count * 384)) gt /= 2;
         k_gridsum<F><<<dim3(nrows + W, 1, G), gt, (gt / 4) * sizeof(xyzz_t), st>>>(ws.d_buckets, B, w_lo, d_rc);
         unsigned ft = TREE_THREADS;                 // half of the elements carry a given bit
         while (ft > 32 && ft / 4 >= std::max(W, nrows)) ft /= 2;

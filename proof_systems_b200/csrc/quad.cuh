@@ -17,12 +17,6 @@
 
 namespace zkb {
 
-__device__ __forceinline__ fe shfl_xor_fe(const fe& a, int m) {
-    fe r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], m);
-    return r;
-}
 __device__ __forceinline__ fe sel_fe(bool c, const fe& a, const fe& b) {
     fe r;
 #pragma unroll

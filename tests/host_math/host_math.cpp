@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../../proof_systems_b200/csrc/curve.cuh"
 #include "../../proof_systems_b200/csrc/ntt_butterfly.cuh"
+#include <vector>
 using namespace zkb;
 
 template <class F> static void mul_(const uint32_t* a, const uint32_t* b, uint32_t* r) {
@@ -105,4 +106,52 @@ template <class F> static void ntt_column_(uint32_t* data, unsigned log_s, const
 extern "C" void hm_ntt_column(int fid, uint32_t* data, unsigned log_s, const uint32_t* small, int radix) {
     if (fid == 0) ntt_column_<FpParams>(data, log_s, small, radix);
     else ntt_column_<FqParams>(data, log_s, small, radix);
+}
+
+// The decimation-in-time schedule of k_ntt_pass (csrc/ntt.cu) on one column of S = 2^log_s rows: bit-reversed load, then — for
+// S >= 64 — the REGISTER stage emulated lane by lane (32 lanes of a warp as arrays, the shuffles as array reads: exactly the
+// per-lane functions the kernel calls), then the shared-memory layers; natural order out.  small = w_1024^i, 512 entries.
+template <class F> static void ntt_column_dit_(uint32_t* data, unsigned log_s, const uint32_t* small32) {
+    const unsigned S = 1u << log_s;
+    fe* x = reinterpret_cast<fe*>(data);
+    const fe* small = reinterpret_cast<const fe*>(small32);
+    std::vector<fe> sm(S);
+    for (unsigned r = 0; r < S; r++) {
+        unsigned i = 0;
+        for (unsigned b = 0; b < log_s; b++) i |= ((r >> b) & 1u) << (log_s - 1 - b);
+        sm[i] = x[r];
+    }
+    unsigned l0 = 0;
+    if (log_s >= 6) {
+        for (unsigned q = 0; q < (S >> 6); q++) {
+            fe a[32], b[32];
+            for (unsigned t = 0; t < 32; t++) { a[t] = sm[(q << 6) + t]; b[t] = sm[(q << 6) + 32 + (t ^ 31u)]; }
+            for (unsigned l = 0; l < 5; l++) {
+                bool a_hi[32];
+                fe tx[32], sa[32], sb[32];
+                for (unsigned t = 0; t < 32; t++) ntt_lane_pre<F>(t, l, a[t], b[t], small, a_hi[t], tx[t], sa[t], sb[t]);
+                for (unsigned t = 0; t < 32; t++) ntt_lane_post<F>(a_hi[t], tx[t], sa[t ^ (1u << l)], sb[t ^ (1u << l)], a[t], b[t]);
+            }
+            fe bn[32];
+            for (unsigned t = 0; t < 32; t++) bn[t] = b[t ^ 31u];
+            for (unsigned t = 0; t < 32; t++) {
+                ntt_lane_last<F>(t, a[t], bn[t], small);
+                sm[(q << 6) + t] = a[t];
+                sm[(q << 6) + 32 + t] = bn[t];
+            }
+        }
+        l0 = 6;
+    }
+    for (unsigned l = l0; l < log_s; l++) {
+        for (unsigned j = 0; j < S / 2; j++) {
+            unsigned i0, tw;
+            ntt_index2_dit(j, l, i0, tw);
+            ntt_bfly2_dit<F>(sm[i0], sm[i0 + (1u << l)], l ? &small[tw] : nullptr);
+        }
+    }
+    for (unsigned k = 0; k < S; k++) x[k] = sm[k];
+}
+extern "C" void hm_ntt_column_dit(int fid, uint32_t* data, unsigned log_s, const uint32_t* small) {
+    if (fid == 0) ntt_column_dit_<FpParams>(data, log_s, small);
+    else ntt_column_dit_<FqParams>(data, log_s, small);
 }

@@ -151,6 +151,24 @@ def test_ntt_tile_layer_schedule_vs_oracle(hm, orc, fid, radix):
         assert np.array_equal(got, orc.ntt(f, a)), (log_s, radix)
 
 
+@pytest.mark.parametrize("fid", [0, 1])
+def test_ntt_dit_schedule_with_register_stage_vs_oracle(hm, orc, fid):
+    """The schedule k_ntt_pass runs since round 2 (csrc/ntt.cu): bit-reversed load, the six layers of span <= 32 in REGISTERS —
+    emulated here lane by lane with the very per-lane functions the kernel calls (ntt_lane_pre / ntt_lane_post / ntt_lane_last,
+    csrc/ntt_butterfly.cuh), the warp shuffles replaced by array reads — then the shared-memory layers; natural order out.
+    Every log_s the tile pass uses must give the oracle's forward NTT."""
+    f = orc.FP if fid == 0 else orc.FQ
+    m = orc.MODULUS[f]
+    w1024 = orc.fe_int(f, orc.root_of_unity(f, 10))
+    small = orc.to_mont(f, orc.ints_to_limbs([pow(w1024, i, m) for i in range(512)]))
+    for log_s in range(0, 11):
+        S = 1 << log_s
+        a = orc.to_mont(f, orc.random_scalars(f, S, seed=200 + log_s))
+        buf = np.ascontiguousarray(a).copy()
+        hm.hm_ntt_column_dit(fid, p32(buf.view(np.uint32)), log_s, p32(small.view(np.uint32)))
+        assert np.array_equal(buf, orc.ntt(f, a)), log_s
+
+
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
 def test_split_product_variants_are_bit_exact(orc, k):
     """field.cuh's ZK_MUL_PLAIN_PER_ROW = k (k products per row as stand-alone wide multiplies + carry adds: the pipe-balancing

@@ -145,3 +145,53 @@ def test_pinned_host_memory_is_transformed_in_place(ctx, orc):
         ctx.ntt_inplace(zk.FQ, view, inverse=True)
         for j in range(batch):
             assert np.array_equal(view[j], orc.ntt(zk.FQ, a[j], inverse=True)), (log_n, j)
+
+
+@pytest.mark.parametrize("fid,log_n", [(0, 21), (1, 22)])
+def test_three_pass_plan_beyond_2_20(ctx, orc, fid, log_n):
+    """kimchi's d8 for a 2^18-gate circuit is 2^21 (kimchi/src/circuits/domains.rs:40-69): transforms beyond 2^20 run as three
+    passes (n = n1 n2 n3).  Forward vs the oracle, inverse(forward) == input, and the zero-padded form."""
+    n = 1 << log_n
+    a = orc.to_mont(fid, orc.random_scalars(fid, n, seed=80 + log_n))
+    f = ctx.ntt(fid, a)
+    assert np.array_equal(f, orc.ntt(fid, a))
+    assert np.array_equal(ctx.ntt(fid, f, inverse=True), a)
+    padded = a.copy()
+    padded[n // 8:] = 0
+    assert np.array_equal(ctx.ntt(fid, a, in_len=n // 8), orc.ntt(fid, padded))
+
+
+def test_out_of_place_device_pipeline(ctx, orc):
+    """zk_ntt_dev_oop + zk_dev_*: witness columns stay on the device from interpolation to evaluation over d8 (prover.rs:370-381 ->
+    constraints.rs:488-507): iFFT(n) in place on 5 columns, then FFT(8n) reading the n coefficients of each column straight from the
+    packed coefficient array (in_stride = n) — no zero-padded copy, no host round trip — equals the oracle's two-step result."""
+    fid, log_n, k = zk.FP, 10, 5
+    n, m = 1 << log_n, 8 << log_n
+    ev = orc.to_mont(fid, orc.random_scalars(fid, k * n, seed=90)).reshape(k, n, 4)
+    d_w = ctx.dev_alloc(ev.nbytes)
+    d_8 = ctx.dev_alloc(k * m * 32)
+    try:
+        ctx.dev_upload(d_w, ev)
+        ctx.ntt_dev(fid, d_w, log_n, batch=k, inverse=True)
+        coeffs = ctx.dev_download(d_w, (k, n, 4))
+        ctx.ntt_dev_oop(fid, d_w, n, n, d_8, log_n + 3, batch=k)
+        got = ctx.dev_download(d_8, (k, m, 4))
+        # the source is untouched by the out-of-place transform
+        assert np.array_equal(ctx.dev_download(d_w, (k, n, 4)), coeffs)
+        for j in range(k):
+            c = orc.ntt(fid, ev[j], inverse=True)
+            assert np.array_equal(coeffs[j], c)
+            pad = np.zeros((m, 4), dtype=np.uint64)
+            pad[:n] = c
+            assert np.array_equal(got[j], orc.ntt(fid, pad)), j
+            assert np.array_equal(got[j][::8], ev[j])                       # d1 sits inside d8 (domains.rs:64-66)
+        # coset variant out of place: the input stays intact as well
+        ctx.ntt_dev_oop(fid, d_w, n, n, d_8, log_n + 1, batch=k, coset=True)
+        got2 = ctx.dev_download(d_8, (k, 2 * n, 4))
+        pad = np.zeros((2 * n, 4), dtype=np.uint64)
+        pad[:n] = coeffs[2]
+        assert np.array_equal(got2[2], orc.ntt(fid, pad, coset=True))
+        assert np.array_equal(ctx.dev_download(d_w, (k, n, 4)), coeffs)
+    finally:
+        ctx.dev_free(d_w)
+        ctx.dev_free(d_8)
