@@ -235,7 +235,7 @@ def main():
 
     import proof_systems_b200 as zk
     from proof_systems_b200._lib import _u64p, check
-    from proof_systems_b200.parallel import ShardedMsm, shard_bounds
+    from proof_systems_b200.parallel import LibraryComm, shard_bounds
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -300,9 +300,10 @@ def main():
     d_poly = torch.from_numpy(poly.view(np.int64)).cuda()
     h_scalars = torch.from_numpy(scalars.view(np.int64)).pin_memory()
     h_poly = torch.from_numpy(poly.view(np.int64).copy()).pin_memory()
-    # N > 1 (weak scaling): the slice sums stay on the device, one all_gather of N x c x 128 bytes rides the context's stream
-    # behind the kernels, the partials are added on the device and read back once (proof_systems_b200/parallel.py)
-    sharded = ShardedMsm(ctx, zk.PALLAS, dev, stream) if world > 1 else None
+    # N > 1 (weak scaling): the exchange is the library's own (csrc/comm.cu): zk_msm_sharded leaves the slice sums on the device,
+    # enqueues ONE ncclAllGather of N x c x 128 bytes from C on the context's stream behind the kernels, adds the partials on the
+    # device and reads them back once.  torch.distributed only carried the 128-byte NCCL id at start-up.
+    comm = LibraryComm(ctx) if world > 1 else None
 
     def msm_host(b, h_sc, n):
         out = np.empty(12, dtype=np.uint64)
@@ -310,13 +311,13 @@ def main():
         return out
 
     def step_resident():
-        if sharded:
-            return sharded(bases, d_scalars.data_ptr(), N_PTS)
+        if comm:
+            return comm.msm(bases, d_scalars.data_ptr(), N_PTS)
         return ctx.msm_dev(bases, d_scalars.data_ptr(), N_PTS)
 
     def step_e2e():
-        if sharded:
-            return sharded(bases, h_scalars.data_ptr(), N_PTS)   # page-locked scalars are read over PCIe by the first kernel
+        if comm:
+            return comm.msm(bases, h_scalars.data_ptr(), N_PTS)   # page-locked scalars are read over PCIe by the first kernel
         return msm_host(bases, h_scalars, N_PTS)
 
     def ntt_resident():
@@ -446,7 +447,7 @@ def main():
         b4, t4 = upload_timed(zk.VESTA, pts4[lo:hi], 16)
         d_sc4 = torch.from_numpy(sc4[lo:hi].view(np.int64)).cuda()
         h_sc4 = torch.from_numpy(sc4[lo:hi].view(np.int64).copy()).pin_memory()
-        sh4 = ShardedMsm(ctx, zk.VESTA, dev, stream)
+        sh4 = comm.msm if comm else (lambda bb, ptr, cnt: ctx.msm_dev(bb, ptr, cnt) if ptr == d_sc4.data_ptr() else msm_host(bb, h_sc4, cnt))
         steps4 = max(3, min(args.steps, 10))
         for _ in range(3):
             r4 = sh4(b4, d_sc4.data_ptr(), hi - lo)
@@ -459,7 +460,7 @@ def main():
         ach4 = MSM_BYTES_PER_POINT * (hi - lo) / (a4 * 1e-3) / 1e9
         extra["cfg4_vesta_2^20_strong"] = {
             "workload": f"2^20-point Vesta MSM split by points over {world} GPU(s) (BASELINE config 4; poly-commitment/benches/msm.rs:92-140), "
-                        "synthetic on-curve bases, uniform Fp scalars; slice sums all_gathered over NCCL and summed on the device",
+                        "synthetic on-curve bases, uniform Fp scalars; slice sums exchanged with one ncclAllGather issued by the library (zk_msm_sharded) and summed on the device",
             "scaling": "strong", "window_bits": b4.window_bits, "points_per_rank": hi - lo, "ms_per_step": t4_res, "value": n4 / (t4_res * 1e-3),
             "unit": "points/s", "e2e_ms_per_step": t4_e2e, "e2e_value": n4 / (t4_e2e * 1e-3), "h2d_bytes_per_step_per_rank": (hi - lo) * 32,
             "stage_ms_rank0": st4,
@@ -467,6 +468,9 @@ def main():
                          "kernel_ms": a4, "algorithmic_bytes": MSM_BYTES_PER_POINT * (hi - lo)}}
         extra["table_build_ms"][f"vesta_2^{(hi - lo).bit_length() - 1}_w{b4.window_bits}"] = round(t4, 3)
     clocks = sampler.stop() if rank == 0 else None
+    if comm:
+        barrier()
+        comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -526,7 +530,7 @@ def main():
         "dtype": "u256 (8 x u32 Montgomery limbs)", "data": "synthetic",
         "config": {
             "workload": "2^16-point Pallas MSM on srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)"
-                        + ("" if world == 1 else f"; rank r adds its own 2^16-scalar slice: one {world * N_PTS}-point MSM, all_gather of {wb} x 128 B slice sums"),
+                        + ("" if world == 1 else f"; every rank holds the same 2^16 bases and its own 2^16 scalars (the sum over ranks of <s_r, g>): weak scaling, ncclAllGather of {wb} x 128 B slice sums issued by the library"),
             "pippenger_window_bits": wb, "window_bits": wb, "resident_table_mib": round(len(bases) * 64 * nwin / 2**20, 1),
             "l2": "256 MiB buffer overwritten between timed iterations (flush)", "result_matches_cpu_oracle": ok, "all_checks_pass": bool(ok_all),
         },

@@ -123,6 +123,22 @@ int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, con
                    int window_bits, void* d_out, size_t capacity_points, unsigned* out_c, unsigned* out_groups);
 int zk_msm_finish_gathered(zk_ctx* ctx, int curve_id, const void* d_all, size_t world, unsigned c, unsigned groups,
                            uint64_t out_xyz[12]);
+/* The same exchange with the communicator owned by the library: one NCCL communicator per context (one per process / GPU), the
+ * all-gather enqueued from C on the context's stream right behind the MSM kernels, the cross-rank sum and the tail as above.
+ *   zk_comm_unique_id   ncclGetUniqueId on one rank; the caller distributes the 128 bytes (MPI, a torch store, a file)
+ *   zk_comm_init_rank   ncclCommInitRank — collective over the `world` ranks
+ *   zk_msm_sharded      one MSM over world x n points: this rank's slice of ITS resident bases with its n scalars (device,
+ *                       page-locked or pageable host memory); collective; every rank receives the identical result.  The reference's
+ *                       1/2/4/8-way split: poly-commitment/benches/msm.rs:92-140.
+ * NCCL is bound at run time (libnccl.so.2 of the host process, else the system's); without it these calls return ZK_ERR_INVALID. */
+typedef struct zk_comm zk_comm;
+int zk_comm_unique_id(uint8_t out_id[128]);
+int zk_comm_init_rank(zk_ctx* ctx, const uint8_t id[128], int world, int rank, zk_comm** out);
+void zk_comm_destroy(zk_comm* comm);
+int zk_comm_world(const zk_comm* comm);
+int zk_comm_rank(const zk_comm* comm);
+int zk_msm_sharded(zk_comm* comm, const zk_bases* bases, size_t off, size_t n, const void* scalars, int scalars_are_mont,
+                   int window_bits, uint64_t out_xyz[12]);
 /* Projective::into_affine / `+` on the host (result handling; multi-GPU partial sums after the all-gather). */
 int zk_jacobian_to_affine(int curve_id, const uint64_t xyz[12], uint64_t out_xy[8]);
 int zk_jacobian_add(int curve_id, const uint64_t a_xyz[12], const uint64_t b_xyz[12], uint64_t out_xyz[12]);
@@ -245,6 +261,20 @@ int zk_srs_open(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, const ui
                 const uint64_t polyscale[4], const uint64_t evalscale[4], const uint64_t* rng_scalars, size_t n_rng_scalars,
                 const zk_open_transcript* transcript, uint64_t* out_lr_xy, size_t lr_capacity_rounds, size_t* out_rounds,
                 uint64_t out_delta_xy[8], uint64_t out_z1[4], uint64_t out_z2[4], uint64_t out_sg_xy[8]);
+
+/* ------------------------------------------------------------------ d8 pipeline, first pointwise evaluator
+ * The permutation part of the quotient polynomial in evaluation form over d8 (m = 2^log_m points), all operands resident on the
+ * device — kimchi/src/circuits/polynomials/permutation.rs:223-357, `perm`:
+ *   out[i] = alpha0 * zkpm[i] * ( z[i] * prod_{k<7} (w_k[i] + gamma + beta * shift_k * x_i)
+ *                               - z[(i + next_shift) mod m] * prod_{k<7} (w_k[i] + gamma + beta * sigma_k[i]) ),     x_i = omega_m^i
+ * d_w: the 7 permuted witness columns over d8, column k at d_w + k * w_stride elements (the output of zk_ntt_dev_oop on the
+ * interpolated columns); d_sigma: permutation_coefficients8 likewise; d_z: z over d8; d_zkpm: permutation_vanishing_polynomial_l
+ * over d8; next_shift = m / n = 8 (z(x omega) is z shifted by eight positions of d8, constraints.rs:497-505); beta, gamma, alpha0
+ * and the 7 shifts (cs.shift) are Montgomery scalars passed by value. */
+int zk_perm_quotient_dev(zk_ctx* ctx, int field_id, unsigned log_m, const void* d_w, size_t w_stride, const void* d_z,
+                         const void* d_sigma, size_t sigma_stride, const void* d_zkpm, const uint64_t beta[4],
+                         const uint64_t gamma[4], const uint64_t alpha0[4], const uint64_t shifts[28], unsigned next_shift,
+                         void* d_out);
 
 /* ------------------------------------------------------------------ diagnostics (tests/test_gpu_field.py, DESIGN.md compute model)
  * Element-wise device field ops on n elements (op: 0 mul, 1 add, 2 sub, 3 inverse of a), host pointers. */

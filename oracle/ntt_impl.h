@@ -128,3 +128,45 @@ static void FN(dft_naive)(FN(t) *out, const FN(t) *in, unsigned log_n, int inver
         for (size_t i = 0; i < n; i++) FN(mul)(&out[i], &out[i], &ninv);
     }
 }
+
+/*
+ * Permutation part of kimchi's quotient polynomial, evaluation form over d8 — restates
+ * kimchi/src/circuits/polynomials/permutation.rs:223-357 (`perm`) point by point:
+ *   shifts[i] = z[i]              * prod_k (w_k[i] + gamma + x_i * beta * shift_k)          (:283-302)
+ *   sigmas[i] = z[(i + 8) mod m]  * prod_k (w_k[i] + gamma + sigma_k[i] * beta)             (:304-328; z_next = lagrange.d8.next.z)
+ *   perm[i]   = (shifts[i] - sigmas[i]) * alpha0 * zkpm[i]                                  (:330-331)
+ * with x_i = omega_m^i the points of d8 (precomputations().poly_x_d1 evaluated over d8), zkpm =
+ * permutation_vanishing_polynomial_l, sigma_k = permutation_coefficients8[k].  Checker of zk_perm_quotient_dev.
+ */
+static void FN(perm_quot)(const FN(t) *w, size_t w_stride, const FN(t) *z, const FN(t) *sigma, size_t sigma_stride, const FN(t) *zkpm,
+                          const FN(t) *beta, const FN(t) *gamma, const FN(t) *alpha0, const FN(t) *shift, unsigned next_shift,
+                          unsigned log_m, FN(t) *out, int threads) {
+    const size_t m = (size_t)1 << log_m;
+    FN(t) omega;
+    FN(root_of_unity)(&omega, log_m);
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t blk = 0; blk < (m + 1023) / 1024; blk++) {
+        FN(t) x;
+        FN(pow_u64)(&x, &omega, blk * 1024);
+        const size_t end = (blk + 1) * 1024 < m ? (blk + 1) * 1024 : m;
+        for (size_t i = blk * 1024; i < end; i++) {
+            FN(t) bx, shifts = z[i], sigmas = z[(i + next_shift) % m];
+            FN(mul)(&bx, beta, &x);
+            for (int k = 0; k < 7; k++) {
+                FN(t) wg, t1, t2;
+                FN(add)(&wg, &w[k * w_stride + i], gamma);
+                FN(mul)(&t1, &bx, &shift[k]);
+                FN(add)(&t1, &t1, &wg);
+                FN(mul)(&shifts, &shifts, &t1);
+                FN(mul)(&t2, &sigma[k * sigma_stride + i], beta);
+                FN(add)(&t2, &t2, &wg);
+                FN(mul)(&sigmas, &sigmas, &t2);
+            }
+            FN(t) d;
+            FN(sub)(&d, &shifts, &sigmas);
+            FN(mul)(&d, &d, alpha0);
+            FN(mul)(&out[i], &d, &zkpm[i]);
+            FN(mul)(&x, &x, &omega);
+        }
+    }
+}

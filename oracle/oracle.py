@@ -207,6 +207,23 @@ def ntt(fid: int, data: np.ndarray, inverse: bool = False, coset: bool = False, 
     return a
 
 
+def perm_quot(fid: int, w, z, sigma, zkpm, beta, gamma, alpha0, shifts, next_shift: int = 8, threads: int = 0) -> np.ndarray:
+    """permutation part of kimchi's quotient over d8 (permutation.rs:223-357): w, sigma [7, m, 4]; z, zkpm [m, 4]; beta, gamma, alpha0 [4];
+    shifts [7, 4]; all Montgomery.  Returns [m, 4]."""
+    w = np.ascontiguousarray(w, dtype=np.uint64).reshape(7, -1, 4)
+    sigma = np.ascontiguousarray(sigma, dtype=np.uint64).reshape(7, -1, 4)
+    m = w.shape[1]
+    log_m = m.bit_length() - 1
+    assert 1 << log_m == m and sigma.shape[1] == m
+    z = np.ascontiguousarray(z, dtype=np.uint64).reshape(m, 4)
+    zkpm = np.ascontiguousarray(zkpm, dtype=np.uint64).reshape(m, 4)
+    out = np.empty((m, 4), dtype=np.uint64)
+    c = lambda a, k: np.ascontiguousarray(a, dtype=np.uint64).reshape(k)
+    lib().orc_perm_quot(fid, _p(w), ctypes.c_size_t(m), _p(z), _p(sigma), ctypes.c_size_t(m), _p(zkpm), _p(c(beta, 4)), _p(c(gamma, 4)), _p(c(alpha0, 4)),
+                        _p(c(shifts, 28)), next_shift, log_m, _p(out), threads)
+    return out
+
+
 def dft_naive(fid: int, data: np.ndarray, inverse: bool = False) -> np.ndarray:
     a = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
     n = a.shape[0]

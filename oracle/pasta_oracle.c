@@ -142,6 +142,19 @@ EXPORT void orc_dft_naive(int fid, const uint64_t *in, uint64_t *out, unsigned l
     else fq_dft_naive((fq_t *)out, (const fq_t *)in, log_n, inverse);
 }
 
+/* permutation part of the quotient over d8 (kimchi/src/circuits/polynomials/permutation.rs:223-357); see ntt_impl.h */
+EXPORT void orc_perm_quot(int fid, const uint64_t *w, size_t w_stride, const uint64_t *z, const uint64_t *sigma, size_t sigma_stride,
+                          const uint64_t *zkpm, const uint64_t *beta, const uint64_t *gamma, const uint64_t *alpha0, const uint64_t *shift,
+                          unsigned next_shift, unsigned log_m, uint64_t *out, int threads) {
+    threads = default_threads(threads);
+    if (fid == 0)
+        fp_perm_quot((const fp_t *)w, w_stride, (const fp_t *)z, (const fp_t *)sigma, sigma_stride, (const fp_t *)zkpm, (const fp_t *)beta,
+                     (const fp_t *)gamma, (const fp_t *)alpha0, (const fp_t *)shift, next_shift, log_m, (fp_t *)out, threads);
+    else
+        fq_perm_quot((const fq_t *)w, w_stride, (const fq_t *)z, (const fq_t *)sigma, sigma_stride, (const fq_t *)zkpm, (const fq_t *)beta,
+                     (const fq_t *)gamma, (const fq_t *)alpha0, (const fq_t *)shift, next_shift, log_m, (fq_t *)out, threads);
+}
+
 /* ---- curve API ---- */
 EXPORT int orc_on_curve(int cid, const uint64_t *xy) {
     if (cid == 0) return pallas_aff_on_curve((const pallas_aff *)xy);

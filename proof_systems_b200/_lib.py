@@ -105,6 +105,12 @@ def lib() -> ctypes.CDLL:
     L.zk_dev_free.argtypes = [vp, vp]
     L.zk_dev_upload.argtypes = [vp, vp, vp, sz]
     L.zk_dev_download.argtypes = [vp, vp, vp, sz]
+    L.zk_perm_quotient_dev.argtypes = [vp, i, u, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp, u, vp]
+    L.zk_comm_unique_id.argtypes = [vp]
+    L.zk_comm_init_rank.argtypes = [vp, vp, i, i, ctypes.POINTER(vp)]
+    L.zk_comm_destroy.argtypes = [vp]
+    L.zk_comm_destroy.restype = None
+    L.zk_msm_sharded.argtypes = [vp, vp, sz, sz, vp, i, i, vp]
     L.zk_srs_open.argtypes = [vp, ctypes.POINTER(OpenPoly), sz, vp, sz, vp, vp, vp, sz, ctypes.POINTER(OpenTranscript), vp, sz,
                               ctypes.POINTER(sz), vp, vp, vp, vp]
     return L
@@ -317,6 +323,14 @@ class Context:
         out = np.empty(shape, dtype=dtype)
         check(lib().zk_dev_download(self._h, _ptr(out), ctypes.c_void_p(d_src), out.nbytes))
         return out
+
+    def perm_quotient_dev(self, field: int, log_m: int, d_w: int, w_stride: int, d_z: int, d_sigma: int, sigma_stride: int, d_zkpm: int, beta, gamma,
+                          alpha0, shifts, d_out: int, next_shift: int = 8):
+        """zk_perm_quotient_dev: the permutation part of the quotient over d8, operands resident on the device"""
+        c = lambda a, k: np.ascontiguousarray(a, dtype=np.uint64).reshape(k)
+        b, g, a0, sh = c(beta, 4), c(gamma, 4), c(alpha0, 4), c(shifts, 28)
+        check(lib().zk_perm_quotient_dev(self._h, field, log_m, ctypes.c_void_p(d_w), w_stride, ctypes.c_void_p(d_z), ctypes.c_void_p(d_sigma), sigma_stride,
+                                         ctypes.c_void_p(d_zkpm), _ptr(b), _ptr(g), _ptr(a0), _ptr(sh), next_shift, ctypes.c_void_p(d_out)))
 
     # ------------------------------------------------------------------ diagnostics
     def field_op(self, field: int, op: str, a, b=None) -> np.ndarray:

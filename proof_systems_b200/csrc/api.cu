@@ -105,25 +105,37 @@ int ctx_ensure(void** p, size_t* cap, size_t bytes) {
     return ZK_OK;
 }
 
-static int ctx_ntt_tables(zk_ctx* ctx, int field, unsigned log_n, bool inverse, const fe** small, const NttTables** tabs) {
+static int ctx_ntt_tables(zk_ctx* lane, int field, unsigned log_n, bool inverse, const fe** small, const NttTables** tabs) {
+    zk_ctx* ctx = ctx_root(lane);                      // one cache per pool; entries are immutable once built
+    std::lock_guard<std::mutex> tl(ctx->tab_mu);
     fe*& sm = ctx->ntt_small[field][inverse ? 1 : 0];
     if (!sm) {
         ZK_CUDA(cudaMalloc(&sm, 512 * sizeof(fe)));
-        int rc = field == ZK_FP ? ntt_build_small_table<FpParams>(sm, inverse, ctx->stream) : ntt_build_small_table<FqParams>(sm, inverse, ctx->stream);
+        int rc = field == ZK_FP ? ntt_build_small_table<FpParams>(sm, inverse, lane->stream) : ntt_build_small_table<FqParams>(sm, inverse, lane->stream);
         if (rc) return rc;
-        ctx->launches += 2;
+        lane->launches += 2;
     }
     unsigned key = (unsigned)field | (inverse ? 2u : 0u) | (log_n << 2);
     auto it = ctx->ntt_tables.find(key);
     if (it == ctx->ntt_tables.end()) {
         NttTables t;
-        int rc = field == ZK_FP ? ntt_build_tables<FpParams>(t, log_n, inverse, ctx->stream) : ntt_build_tables<FqParams>(t, log_n, inverse, ctx->stream);
+        int rc = field == ZK_FP ? ntt_build_tables<FpParams>(t, log_n, inverse, lane->stream) : ntt_build_tables<FqParams>(t, log_n, inverse, lane->stream);
         if (rc) return rc;
-        ctx->launches += t.full ? 8 : 7;
+        lane->launches += t.full ? 8 : 7;
         it = ctx->ntt_tables.emplace(key, t).first;
     }
     *small = sm;
     *tabs = &it->second;
+    return ZK_OK;
+}
+
+// the unscaled twiddle tables of a forward / inverse transform (pointwise evaluators take x_i = w^i from them)
+int ctx_ntt_table_ptrs(zk_ctx* ctx, int field, unsigned log_n, bool inverse, const fe** ulo, const fe** mid, const fe** hi2) {
+    const fe* small;
+    const NttTables* tabs;
+    int rc = ctx_ntt_tables(ctx, field, log_n, inverse, &small, &tabs);
+    if (rc) return rc;
+    *ulo = tabs->ulo; *mid = tabs->mid; *hi2 = tabs->hi2;
     return ZK_OK;
 }
 
@@ -167,6 +179,51 @@ int ctx_ntt_device_oop(zk_ctx* ctx, int field, const fe* d_in, size_t in_bs, fe*
 
 int ctx_ntt_device(zk_ctx* ctx, int field, fe* d_data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
     return ctx_ntt_device_oop(ctx, field, d_data, (size_t)1 << (log_n > 62 ? 0 : log_n), d_data, log_n, batch, in_len, inverse, coset);
+}
+
+// ---------------------------------------------------------------------------------------------- lanes
+static int ctx_init_lane(zk_ctx* c, int device_id) {
+    c->device = device_id;
+    cudaError_t se = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) { zk_set_error("cudaStreamCreate: %s", cudaGetErrorString(se)); return ZK_ERR_CUDA; }
+    c->stream = c->own_stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->ws.sm_count = prop.multiProcessorCount;
+    return ZK_OK;
+}
+
+int ctx_acquire_lane(zk_ctx* ctx, LaneLock& out) {
+    ctx = ctx_root(ctx);
+    const bool pinned = ctx->stream != ctx->own_stream || ctx->profile || ctx->n_lanes <= 1;
+    if (pinned) {
+        out.lane = ctx;
+        out.lk = std::unique_lock<std::mutex>(ctx->mu);
+        return ZK_OK;
+    }
+    std::vector<zk_ctx*> lanes;
+    unsigned start;
+    {
+        std::lock_guard<std::mutex> pl(ctx->pool_mu);
+        while ((int)ctx->children.size() + 1 < ctx->n_lanes) {
+            zk_ctx* c = new zk_ctx();
+            c->parent = ctx;
+            if (cudaSetDevice(ctx->device) != cudaSuccess || ctx_init_lane(c, ctx->device) != ZK_OK) { delete c; break; }
+            c->batch = ctx->batch; c->ws.chunk = ctx->ws.chunk; c->ws.wave_threads = ctx->ws.wave_threads;
+            ctx->children.push_back(c);
+        }
+        lanes.push_back(ctx);
+        lanes.insert(lanes.end(), ctx->children.begin(), ctx->children.end());
+        start = ctx->rr++;
+    }
+    for (size_t k = 0; k < lanes.size(); k++) {
+        zk_ctx* l = lanes[(start + k) % lanes.size()];
+        std::unique_lock<std::mutex> lk(l->mu, std::try_to_lock);
+        if (lk.owns_lock()) { out.lane = l; out.lk = std::move(lk); return ZK_OK; }
+    }
+    zk_ctx* l = lanes[start % lanes.size()];
+    out.lane = l;
+    out.lk = std::unique_lock<std::mutex>(l->mu);
+    return ZK_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- diagnostics kernels
@@ -250,18 +307,15 @@ int zk_ctx_create(int device_id, zk_ctx** out) {
     if (device_id < 0 || device_id >= n) { zk_set_error("ctx_create: device %d outside [0, %d)", device_id, n); return ZK_ERR_INVALID; }
     ZK_CUDA(cudaSetDevice(device_id));
     zk_ctx* ctx = new zk_ctx();
-    ctx->device = device_id;
-    cudaError_t se = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    if (se != cudaSuccess) { zk_set_error("cudaStreamCreate: %s", cudaGetErrorString(se)); delete ctx; return ZK_ERR_CUDA; }
-    ctx->stream = ctx->own_stream;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->ws.sm_count = prop.multiProcessorCount;
+    if (int rc = ctx_init_lane(ctx, device_id)) { delete ctx; return rc; }
     *out = ctx;
     return ZK_OK;
 }
 
 void zk_ctx_destroy(zk_ctx* ctx) {
     if (!ctx) return;
+    for (zk_ctx* c : ctx->children) zk_ctx_destroy(c);
+    ctx->children.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     msm_workspace_free(ctx->ws);
@@ -289,7 +343,12 @@ int zk_ctx_set_stream(zk_ctx* ctx, void* cuda_stream) {
     return ZK_OK;
 }
 
-uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t zk_ctx_launch_count(const zk_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (const zk_ctx* c : ctx->children) n += c->launches;
+    return n;
+}
 
 int zk_ctx_set_profile(zk_ctx* ctx, int enabled) {
     if (!ctx) { zk_set_error("set_profile: ctx is null"); return ZK_ERR_INVALID; }
@@ -305,16 +364,24 @@ int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value) {
     if (!strcmp(name, "msm_chunk")) {
         if (value < 0 || value > 4096) { zk_set_error("set_option: msm_chunk %ld outside [0, 4096]", value); return ZK_ERR_INVALID; }
         ctx->ws.chunk = (uint32_t)value;
+        for (zk_ctx* c : ctx->children) c->ws.chunk = (uint32_t)value;
+        return ZK_OK;
+    }
+    if (!strcmp(name, "ctx_lanes")) {
+        if (value < 1 || value > 16) { zk_set_error("set_option: ctx_lanes %ld outside [1, 16]", value); return ZK_ERR_INVALID; }
+        ctx->n_lanes = (int)value;       // lanes already created stay allocated; fewer are used from now on
         return ZK_OK;
     }
     if (!strcmp(name, "msm_batch")) {
         if (value < 1 || value > (long)MSM_MAX_BATCH) { zk_set_error("set_option: msm_batch %ld outside [1, %u]", value, MSM_MAX_BATCH); return ZK_ERR_INVALID; }
         ctx->batch = (int)value;
+        for (zk_ctx* c : ctx->children) c->batch = (int)value;
         return ZK_OK;
     }
     if (!strcmp(name, "msm_wave_threads")) {
         if (value < 0 || value > 2048) { zk_set_error("set_option: msm_wave_threads %ld outside [0, 2048]", value); return ZK_ERR_INVALID; }
         ctx->ws.wave_threads = (uint32_t)value;
+        for (zk_ctx* c : ctx->children) c->ws.wave_threads = (uint32_t)value;
         return ZK_OK;
     }
     zk_set_error("set_option: unknown option '%s'", name);
@@ -439,16 +506,18 @@ int zk_points_synthetic(zk_ctx* ctx, int curve_id, uint64_t seed, size_t n, uint
 // ---------------------------------------------------------------------------------------------- MSM
 int zk_msm_dev(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* d_scalars, int scalars_are_mont, int window_bits, uint64_t out_xyz[12]) {
     if (!ctx || !bases || !out_xyz || (!d_scalars && n)) { zk_set_error("msm: null argument"); return ZK_ERR_INVALID; }
-    if (bases->ctx != ctx) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
+    if (ctx_root(bases->ctx) != ctx_root(ctx)) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));
     return ctx_msm_device(ctx, bases, off, n, (const fe*)d_scalars, scalars_are_mont, window_bits, out_xyz);
 }
 
-int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, size_t k, int scalars_are_mont, int window_bits, uint64_t* out_xyz) {
-    if (!ctx || !bases || (!out_xyz && k) || (!scalars && n && k)) { zk_set_error("msm: null argument"); return ZK_ERR_INVALID; }
-    if (bases->ctx != ctx) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
+int zk_msm_batch(zk_ctx* root, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, size_t k, int scalars_are_mont, int window_bits, uint64_t* out_xyz) {
+    if (!root || !bases || (!out_xyz && k) || (!scalars && n && k)) { zk_set_error("msm: null argument"); return ZK_ERR_INVALID; }
+    if (ctx_root(bases->ctx) != ctx_root(root)) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
+    LaneLock ll;                             // host pointers in, host result out: any free lane of the pool
+    if (int rc = ctx_acquire_lane(root, ll)) return rc;
+    zk_ctx* ctx = ll.lane;
     ZK_CUDA(cudaSetDevice(ctx->device));
     if (k == 0) return ZK_OK;
     // Scalars in page-locked (cudaHostAlloc / cudaHostRegister) memory are read by the recode kernel straight over PCIe
@@ -472,14 +541,12 @@ int zk_msm_batch(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const
 
 // Multi-GPU sharding: this rank's MSM is left on the device as its slice sums and nothing is synchronised, so
 // the caller can enqueue the all-gather on the same stream while the kernels still run.
-int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* scalars, int scalars_are_mont, int window_bits,
+static int msm_partial_impl(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* scalars, int scalars_are_mont, int window_bits,
                    void* d_out, size_t capacity_points, unsigned* out_c, unsigned* out_groups) {
     if (!ctx || !bases || !d_out || !out_c || !out_groups || (!scalars && n)) { zk_set_error("msm_partial: null argument"); return ZK_ERR_INVALID; }
-    if (bases->ctx != ctx) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
+    if (ctx_root(bases->ctx) != ctx_root(ctx)) { zk_set_error("msm: bases belong to another context"); return ZK_ERR_INVALID; }
     if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
     if (n == 0) { zk_set_error("msm_partial: empty slice"); return ZK_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ZK_CUDA(cudaSetDevice(ctx->device));
     const fe* d_sc = nullptr;
     cudaPointerAttributes attr;
     const bool known = cudaPointerGetAttributes(&attr, scalars) == cudaSuccess;
@@ -512,13 +579,11 @@ int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, con
 
 // d_all: `world` gathered partials of zk_msm_partial (device, world x groups*c points, same shape on every rank).  Sums them
 // per slice on the device, copies groups*c points to the host and finishes the O(c) tail there.
-int zk_msm_finish_gathered(zk_ctx* ctx, int curve_id, const void* d_all, size_t world, unsigned c, unsigned groups, uint64_t out_xyz[12]) {
+static int msm_finish_gathered_impl(zk_ctx* ctx, int curve_id, const void* d_all, size_t world, unsigned c, unsigned groups, uint64_t out_xyz[12]) {
     if (!ctx || !d_all || !out_xyz || world == 0) { zk_set_error("msm_finish_gathered: null argument"); return ZK_ERR_INVALID; }
     if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("msm_finish_gathered: unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
     const size_t count = (size_t)c * groups;
     if (count == 0 || count > 4096) { zk_set_error("msm_finish_gathered: bad shape c = %u, groups = %u", c, groups); return ZK_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ZK_CUDA(cudaSetDevice(ctx->device));
     int rc = ctx_ensure((void**)&ctx->d_gather_sum, &ctx->cap_gather_sum, count * sizeof(xyzz_t));
     if (rc) return rc;
     if (ctx->cap_h_gather < count) {
@@ -536,6 +601,20 @@ int zk_msm_finish_gathered(zk_ctx* ctx, int curve_id, const void* d_all, size_t 
     host::hxyzz r = curve_id == ZK_PALLAS ? msm_finish_t<host::HFp>(ctx->h_gather, c, groups) : msm_finish_t<host::HFq>(ctx->h_gather, c, groups);
     xyzz_to_jac_out(curve_id, r, out_xyz);
     return ZK_OK;
+}
+
+int zk_msm_partial(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* scalars, int scalars_are_mont, int window_bits,
+                   void* d_out, size_t capacity_points, unsigned* out_c, unsigned* out_groups) {
+    if (!ctx) { zk_set_error("msm_partial: null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    return msm_partial_impl(ctx, bases, off, n, scalars, scalars_are_mont, window_bits, d_out, capacity_points, out_c, out_groups);
+}
+int zk_msm_finish_gathered(zk_ctx* ctx, int curve_id, const void* d_all, size_t world, unsigned c, unsigned groups, uint64_t out_xyz[12]) {
+    if (!ctx) { zk_set_error("msm_finish_gathered: null argument"); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    return msm_finish_gathered_impl(ctx, curve_id, d_all, world, c, groups, out_xyz);
 }
 
 int zk_msm(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const uint64_t* scalars, int scalars_are_mont, int window_bits, uint64_t out_xyz[12]) {
@@ -635,10 +714,12 @@ int zk_dev_download(zk_ctx* ctx, void* dst, const void* d_src, size_t bytes) {
     return ZK_OK;
 }
 
-int zk_ntt_batch(zk_ctx* ctx, int field_id, uint64_t* data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
-    if (!ctx || (!data && batch)) { zk_set_error("ntt: null argument"); return ZK_ERR_INVALID; }
+int zk_ntt_batch(zk_ctx* root, int field_id, uint64_t* data, unsigned log_n, size_t batch, size_t in_len, int inverse, int coset) {
+    if (!root || (!data && batch)) { zk_set_error("ntt: null argument"); return ZK_ERR_INVALID; }
     if (log_n > NTT_MAX_LOG_N) { zk_set_error("ntt: log_n %u > %u not supported", log_n, NTT_MAX_LOG_N); return ZK_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    LaneLock ll;                             // host pointers in and out: any free lane of the pool
+    if (int rc0 = ctx_acquire_lane(root, ll)) return rc0;
+    zk_ctx* ctx = ll.lane;
     ZK_CUDA(cudaSetDevice(ctx->device));
     if (batch == 0) return ZK_OK;
     const size_t n = (size_t)1 << log_n, poly_bytes = n * sizeof(fe), bytes = batch * poly_bytes;
@@ -768,3 +849,13 @@ int zk_debug_mul_throughput(zk_ctx* ctx, int field_id, unsigned iters, double* o
 }
 
 }  // extern "C"
+
+namespace zkb {
+int ctx_msm_partial_nolock(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const void* scalars, int scalars_are_mont, int window_bits,
+                           void* d_out, size_t capacity_points, unsigned* out_c, unsigned* out_groups) {
+    return msm_partial_impl(ctx, bases, off, n, scalars, scalars_are_mont, window_bits, d_out, capacity_points, out_c, out_groups);
+}
+int ctx_msm_finish_gathered_nolock(zk_ctx* ctx, int curve_id, const void* d_all, size_t world, unsigned c, unsigned groups, uint64_t out_xyz[12]) {
+    return msm_finish_gathered_impl(ctx, curve_id, d_all, world, c, groups, out_xyz);
+}
+}  // namespace zkb

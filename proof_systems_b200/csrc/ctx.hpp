@@ -1,12 +1,26 @@
 // ctx.hpp — the objects behind the opaque handles of include/zkb200.h.
 #pragma once
 #include <map>
+#include <memory>
 #include <mutex>
+#include <vector>
 
 #include "msm.cuh"
 #include "ntt.cuh"
 
 struct zk_ctx {
+    // Concurrency (SURVEY.md §8b "Threading": SRS is Sync + Send, 15 rayon workers commit at once, kimchi/src/prover.rs:329-351):
+    // a context is a small POOL of lanes — itself plus up to n_lanes - 1 children, each a full context with its own stream,
+    // scratch and mutex.  Host-pointer entry points (zk_msm*, zk_ntt / zk_ntt_batch, zk_srs_commit_*) take whichever lane is
+    // free, so independent calls from different threads overlap on the device; the *_dev entry points (device pointers, caller
+    // ordered) and handle-bound calls stay on the primary lane.  A caller-provided stream (zk_ctx_set_stream) or profiling mode
+    // pins everything to the primary lane.  Resident bases and twiddle tables are shared, read-only.
+    zk_ctx* parent = nullptr;                  // children point at the primary lane
+    std::vector<zk_ctx*> children;
+    int n_lanes = 4;                           // zk_ctx_set_option("ctx_lanes")
+    unsigned rr = 0;                           // round-robin start of the next acquisition (guarded by pool_mu)
+    std::mutex pool_mu;                        // children list
+    std::mutex tab_mu;                         // NTT table cache of the primary lane (shared by all lanes)
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::mutex mu;                       // a context serialises its calls (SRS: Sync + Send, SURVEY.md §8b "Threading")
@@ -42,6 +56,14 @@ struct zk_bases {
 };
 
 namespace zkb {
+// the lane a host-pointer call runs on, locked for the call's duration
+struct LaneLock {
+    zk_ctx* lane = nullptr;
+    std::unique_lock<std::mutex> lk;
+};
+int ctx_acquire_lane(zk_ctx* ctx, LaneLock& out);
+inline zk_ctx* ctx_root(zk_ctx* c) { return c && c->parent ? c->parent : c; }
+inline const zk_ctx* ctx_root(const zk_ctx* c) { return c && c->parent ? c->parent : c; }
 int ctx_msm_device(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* d_scalars, int mont, int window_bits,
                    uint64_t out_xyz[12]);
 int ctx_ensure(void** p, size_t* cap, size_t bytes);

@@ -202,7 +202,7 @@ extern "C" {
 
 int zk_ipa_begin(zk_ctx* ctx, const zk_bases* bases, const uint64_t* a_mont, const uint64_t* b_mont, size_t n, zk_ipa** out) {
     if (!ctx || !bases || !a_mont || !b_mont || !out) { zk_set_error("ipa_begin: null argument"); return ZK_ERR_INVALID; }
-    if (bases->ctx != ctx) { zk_set_error("ipa_begin: bases belong to another context"); return ZK_ERR_INVALID; }
+    if (ctx_root(bases->ctx) != ctx_root(ctx)) { zk_set_error("ipa_begin: bases belong to another context"); return ZK_ERR_INVALID; }
     if (n < 2) { zk_set_error("ipa_begin: n must be a power of two >= 2 (the reference pads to a power of two, ipa.rs:848-850)"); return ZK_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));

@@ -43,11 +43,12 @@ template <class F> __global__ void k_pow_table(fe* out, const fe* base, const fe
     store_fe(out + i, r);
 }
 
-// full[k * n2 + col] = w^(col * k) (* n^-1): the inter-pass twiddles of the two-pass plan in the layout pass 1 stores to
-template <class F> __global__ void k_full_table(fe* full, const fe* __restrict__ lo, const fe* __restrict__ mid, unsigned log_n2, size_t n) {
+// full[col * n1 + k] = w^(col * k) (* n^-1): the inter-pass twiddles of the two-pass plan, one contiguous run of n1 entries per
+// tile (= column) of pass 1, so a tile streams its twiddles with fully coalesced loads
+template <class F> __global__ void k_full_table(fe* full, const fe* __restrict__ lo, const fe* __restrict__ mid, unsigned log_n1, size_t n) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const unsigned col = (unsigned)(idx & (((size_t)1 << log_n2) - 1)), k = (unsigned)(idx >> log_n2);
+    const unsigned k = (unsigned)(idx & (((size_t)1 << log_n1) - 1)), col = (unsigned)(idx >> log_n1);
     const unsigned e = col * k;          // < n <= 2^22
     fe tw = load_fe_nc(lo + (e & 1023));
     if (e >> 10) tw = fe_mul<F>(tw, load_fe_nc(mid + (e >> 10)));
@@ -81,9 +82,9 @@ template <class F> int ntt_build_tables(NttTables& t, unsigned log_n, bool inver
     t.full = nullptr;
     if (log_n > NTT_MAX_LOG_SUB && log_n <= NTT_FULL_TABLE_MAX_LOG) {
         const size_t n = (size_t)1 << log_n;
-        const unsigned log_n2 = log_n - (log_n + 1) / 2;
+        const unsigned log_n1 = (log_n + 1) / 2;
         ZK_CUDA(cudaMalloc(&t.full, n * sizeof(fe)));
-        k_full_table<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.full, t.lo, t.mid, log_n2, n);
+        k_full_table<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.full, t.lo, t.mid, log_n1, n);
     }
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaStreamSynchronize(st));
@@ -103,7 +104,7 @@ void ntt_free_tables(NttTables& t) {
 // store; the bit-reversed write of the load hits rows S/32 apart, which the padding spreads over the 32 banks: conflict free.
 __device__ __forceinline__ unsigned ntt_pad(unsigned i) { return i + (i >> 5); }
 
-template <class F> __global__ void __launch_bounds__(128) k_ntt_pass(NttPassParams p) {
+template <class F> __global__ void __launch_bounds__(128, 6) k_ntt_pass(NttPassParams p) {
     extern __shared__ uint32_t sm[];
     const unsigned S = 1u << p.log_s, SP = S + (S >> 5) + 1;
     const unsigned tid = threadIdx.x, nthr = blockDim.x;
@@ -114,15 +115,25 @@ template <class F> __global__ void __launch_bounds__(128) k_ntt_pass(NttPassPara
     const size_t out_off = t_hi * p.out_hi + t_lo * p.out_lo;
     fe* out = p.out + (size_t)blockIdx.y * p.out_bs + out_off;
 
-    // load, zero-padded by position, written in bit-reversed row order
-    for (unsigned r = tid; r < S; r += nthr) {
-        const size_t pos = p.pos_is_row ? (size_t)r : in_off + r * p.in_rs;
-        fe v = fe_zero();
-        if (pos < p.in_len) v = load_fe(in + r * p.in_rs);
-        const unsigned i = p.log_s ? (__brev(r) >> (32 - p.log_s)) : 0;
-        uint32_t* dst = sm + ntt_pad(i);
+    // load, zero-padded by position, written in bit-reversed row order; four independent loads in flight per thread
+    for (unsigned r0 = tid; r0 < S; r0 += 4 * nthr) {
+        fe v[4];
 #pragma unroll
-        for (int l = 0; l < 8; l++) dst[l * SP] = v.v[l];
+        for (int u = 0; u < 4; u++) {
+            const unsigned r = r0 + u * nthr;
+            const size_t pos = p.pos_is_row ? (size_t)r : in_off + r * p.in_rs;
+            v[u] = fe_zero();
+            if (r < S && pos < p.in_len) v[u] = load_fe(in + r * p.in_rs);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned r = r0 + u * nthr;
+            if (r >= S) break;
+            const unsigned i = p.log_s ? (__brev(r) >> (32 - p.log_s)) : 0;
+            uint32_t* dst = sm + ntt_pad(i);
+#pragma unroll
+            for (int l = 0; l < 8; l++) dst[l * SP] = v[u].v[l];
+        }
     }
     __syncthreads();
 
@@ -172,25 +183,37 @@ template <class F> __global__ void __launch_bounds__(128) k_ntt_pass(NttPassPara
         __syncthreads();
     }
 
-    // store: natural order; inter-pass twiddle, scaling and transposition fused
+    // store: natural order; inter-pass twiddle, scaling and transposition fused.  Four twiddle loads in flight per thread.
     const size_t tw_col = p.tw_by_lo ? t_lo : tau;
-    for (unsigned k = tid; k < S; k += nthr) {
-        const uint32_t* src = sm + ntt_pad(k);
-        fe v;
-#pragma unroll
-        for (int l = 0; l < 8; l++) v.v[l] = src[l * SP];
-        const size_t o = k * p.out_rs;
+    for (unsigned k0 = tid; k0 < S; k0 += 4 * nthr) {
+        fe tw[4];
         if (p.tw_full) {
-            v = fe_mul<F>(v, load_fe_nc(p.tw_full + out_off + o));
-        } else if (p.lo) {
-            const unsigned e = (unsigned)tw_col * k;                  // < 2^30
-            fe tw = load_fe_nc(p.lo + (e & 1023));
-            if ((e >> 10) & 1023) tw = fe_mul<F>(tw, load_fe_nc(p.mid + ((e >> 10) & 1023)));
-            if (e >> 20) tw = fe_mul<F>(tw, load_fe_nc(p.hi2 + (e >> 20)));
-            v = fe_mul<F>(v, tw);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned k = k0 + u * nthr;
+                if (k < S) tw[u] = load_fe_nc(p.tw_full + (tau << p.log_s) + k);
+            }
         }
-        if (p.scale) v = fe_mul<F>(v, load_fe_nc(p.scale));
-        store_fe(out + o, v);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned k = k0 + u * nthr;
+            if (k >= S) break;
+            const uint32_t* src = sm + ntt_pad(k);
+            fe v;
+#pragma unroll
+            for (int l = 0; l < 8; l++) v.v[l] = src[l * SP];
+            if (p.tw_full) {
+                v = fe_mul<F>(v, tw[u]);
+            } else if (p.lo) {
+                const unsigned e = (unsigned)tw_col * k;                  // < 2^30
+                fe t = load_fe_nc(p.lo + (e & 1023));
+                if ((e >> 10) & 1023) t = fe_mul<F>(t, load_fe_nc(p.mid + ((e >> 10) & 1023)));
+                if (e >> 20) t = fe_mul<F>(t, load_fe_nc(p.hi2 + (e >> 20)));
+                v = fe_mul<F>(v, t);
+            }
+            if (p.scale) v = fe_mul<F>(v, load_fe_nc(p.scale));
+            store_fe(out + k * p.out_rs, v);
+        }
     }
 }
 

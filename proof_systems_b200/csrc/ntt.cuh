@@ -34,7 +34,7 @@ struct NttTables {
     fe* hi2 = nullptr;   // [1024] w_n^(+-2^20 i)
     fe* clo = nullptr;   // [1024] g^(+-i)              coset powers
     fe* chi = nullptr;   // [1024] g^(+-1024 i)
-    fe* full = nullptr;  // [n]    w_n^(+-(col * k)) (inverse: times n^-1) at index k * n2 + col, the layout pass 1 stores to; or null
+    fe* full = nullptr;  // [n]    w_n^(+-(col * k)) (inverse: times n^-1) at index col * n1 + k: contiguous per tile of pass 1; or null
 };
 
 // One pass = independent S-point transforms of columns ("tiles").  Tile tau = (t_hi << split_log) | t_lo of polynomial b reads
@@ -44,7 +44,7 @@ struct NttPassParams {
     const fe* in;
     fe* out;
     const fe* small;       // [512] w_1024^(+-i)
-    const fe* tw_full;     // pass twiddle: n-entry table indexed like the output, or
+    const fe* tw_full;     // pass twiddle: n-entry table, entry (tau << log_s) + k, or
     const fe* lo;          //               three 1024-entry tables, exponent e = (tw_by_lo ? t_lo : tau) * k,
     const fe* mid;         //               w^e = lo[e & 1023] * mid[(e >> 10) & 1023] * hi2[e >> 20]; all null: no twiddle
     const fe* hi2;

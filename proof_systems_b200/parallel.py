@@ -87,3 +87,42 @@ def all_gather_point_sum(curve: int, partial_xyz: np.ndarray, group=None, device
     gathered = torch.empty((world, 12), dtype=torch.int64, device=mine.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
     return jacobian_sum(curve, gathered.cpu().numpy().view(np.uint64))
+
+
+class LibraryComm:
+    """The exchange owned by the library (csrc/comm.cu): one NCCL communicator per context, created from a 128-byte unique id that
+    rank 0 obtains from zk_comm_unique_id and the ranks share through `torch.distributed` (plumbing only: a broadcast of 128
+    bytes at start-up); afterwards zk_msm_sharded runs the MSM kernels, ncclAllGather and the cross-rank sum from C on the
+    context's stream — no Python, no torch collective on the data path."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes
+
+        from ._lib import check, lib
+        self.ctx = ctx
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            check(lib().zk_comm_unique_id(ctypes.c_void_p(uid.ctypes.data)))
+        if self.world > 1:
+            t = torch.from_numpy(uid).cuda()
+            dist.broadcast(t, src=0, group=group)
+            uid = t.cpu().numpy()
+        self._h = ctypes.c_void_p()
+        check(lib().zk_comm_init_rank(ctx._h, ctypes.c_void_p(uid.ctypes.data), self.world, self.rank, ctypes.byref(self._h)))
+
+    def msm(self, bases, scalars_ptr: int, n: int, off: int = 0, mont: bool = False, window_bits: int = 0) -> np.ndarray:
+        """one MSM over world x n points (this rank's slice); collective; Jacobian [12], identical on every rank"""
+        import ctypes
+
+        from ._lib import _u64p, check, lib
+        out = np.empty(12, dtype=np.uint64)
+        check(lib().zk_msm_sharded(self._h, bases._h, off, n, ctypes.c_void_p(scalars_ptr), int(mont), window_bits, out.ctypes.data_as(_u64p)))
+        return out
+
+    def close(self):
+        from ._lib import lib
+        if getattr(self, "_h", None):
+            lib().zk_comm_destroy(self._h)
+            self._h = None

@@ -300,3 +300,59 @@ def test_synthetic_points_are_on_the_curve_and_deterministic(ctx, orc):
         b = ctx.upload_bases(cid, p, window_bits=-1)
         assert np.array_equal(ctx.msm_affine(b, sc), orc.msm(cid, p, sc))
         b.free()
+
+
+def test_concurrent_host_callers_overlap_on_the_lane_pool(orc, pallas_srs):
+    """kimchi/src/prover.rs:329-351: 15 rayon workers call commit_evaluations_non_hiding at once on ONE shared SRS.  A context is a
+    pool of lanes (csrc/ctx.hpp): independent host-pointer calls from different threads run concurrently on the device — every
+    result equals the serial one, and the 15 calls take clearly less wall-clock time than one after the other."""
+    import threading
+    import time
+    G = pallas_srs
+    n, k = 1 << 14, 15
+    c = zk.Context(0)
+    try:
+        bases = c.upload_bases(zk.PALLAS, G.g[:n], window_bits=-1)
+        sc = [orc.random_scalars(G.scalar, n, seed=300 + j) for j in range(k)]
+        serial = [c.msm(bases, sc[j]) for j in range(k)]                      # also warms every code path up
+        c.set_option("ctx_lanes", 1)
+        t0 = time.perf_counter()
+        for j in range(k):
+            c.msm(bases, sc[j])
+        t_serial = time.perf_counter() - t0
+        c.set_option("ctx_lanes", 4)
+        out = [None] * k
+
+        def work(j):
+            out[j] = c.msm(bases, sc[j])
+        for _ in range(2):                                                    # first round creates the lanes and their scratch
+            th = [threading.Thread(target=work, args=(j,)) for j in range(k)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            t_pool = time.perf_counter() - t0
+        for j in range(k):
+            assert np.array_equal(out[j], serial[j]), j
+        assert t_pool < 0.75 * t_serial, (t_pool, t_serial)
+        bases.free()
+    finally:
+        c.close()
+
+
+def test_library_owned_communicator_single_rank(ctx, orc, pallas_srs):
+    """zk_comm_* / zk_msm_sharded with a world of one: the NCCL communicator is created inside the library (csrc/comm.cu) and the
+    sharded entry point returns the plain MSM."""
+    from proof_systems_b200.parallel import LibraryComm
+    G = pallas_srs
+    n = 4096
+    comm = LibraryComm(ctx)
+    try:
+        bases = ctx.upload_bases(zk.PALLAS, G.g[:n], window_bits=-1)
+        sc = orc.random_scalars(G.scalar, n, seed=77)
+        got = zk.jacobian_to_affine(zk.PALLAS, comm.msm(bases, sc.ctypes.data, n))
+        assert np.array_equal(got, orc.msm(zk.PALLAS, G.g[:n], sc))
+        bases.free()
+    finally:
+        comm.close()
