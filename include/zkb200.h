@@ -188,8 +188,12 @@ size_t zk_srs_max_poly_size(const zk_srs* srs);
 int zk_srs_add_lagrange_basis(zk_srs* srs, size_t domain_size, const uint64_t* basis_xy, int window_bits);
 /* SRS::get_lagrange_basis_from_domain_size -> SRS::lagrange_basis (ipa.rs:780-788, 1065-1172) computed ON THE DEVICE from the
  * resident generators: inverse FFT over group elements + normalisation, registered for commit_evaluations_non_hiding.
- * domain_size: power of two <= |g| (single-chunk bases).  zk_srs_get_lagrange_basis copies it to the host (n x 8 u64). */
+ * domain_size: a power of two.  A domain larger than |g| gives CHUNKED bases (ipa.rs:1145-1171): ceil(domain / |g|) partial
+ * commitments per element (zk_srs_lagrange_basis_chunks), stored chunk-major — chunk c's domain_size points come first for c = 0,
+ * and PolyComm i of the reference is (chunk_c[i])_c.  zk_srs_get_lagrange_basis copies all chunks to the host (chunks x n x 8 u64);
+ * zk_srs_add_lagrange_basis takes the same layout; zk_srs_commit_evaluations_non_hiding then writes `chunks` points. */
 int zk_srs_lagrange_basis(zk_srs* srs, size_t domain_size, int window_bits);
+size_t zk_srs_lagrange_basis_chunks(const zk_srs* srs, size_t domain_size);
 int zk_srs_get_lagrange_basis(zk_srs* srs, size_t domain_size, uint64_t* out_xy, size_t capacity_points);
 int zk_srs_commit_non_hiding(zk_srs* srs, const uint64_t* coeffs_mont, size_t len, size_t num_chunks, uint64_t* out_xy,
                              size_t out_capacity, size_t* out_chunks);

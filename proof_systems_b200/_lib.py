@@ -81,6 +81,8 @@ def lib() -> ctypes.CDLL:
     L.zk_srs_add_lagrange_basis.argtypes = [vp, sz, vp, i]
     L.zk_srs_lagrange_basis.argtypes = [vp, sz, i]
     L.zk_srs_get_lagrange_basis.argtypes = [vp, sz, _u64p, sz]
+    L.zk_srs_lagrange_basis_chunks.argtypes = [vp, sz]
+    L.zk_srs_lagrange_basis_chunks.restype = sz
     L.zk_srs_commit_non_hiding.argtypes = [vp, vp, sz, sz, _u64p, sz, ctypes.POINTER(sz)]
     L.zk_srs_commit_evaluations_non_hiding.argtypes = [vp, sz, vp, sz, _u64p]
     L.zk_srs_commit_evaluations_batch.argtypes = [vp, sz, vp, sz, _u64p]

@@ -53,6 +53,12 @@ static void xyzz_to_jac_out(int curve, const host::hxyzz& p, uint64_t out[12]) {
 
 int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
                  uint64_t* out_xyz, const affine_t* d_extra, size_t n_extra) {
+    std::vector<size_t> offs(k, off);
+    return ctx_msm_many_offs(ctx, bases, offs.data(), n, d_scalars, k, mont, window_bits, out_xyz, d_extra, n_extra);
+}
+
+int ctx_msm_many_offs(zk_ctx* ctx, const zk_bases* bases, const size_t* offs, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
+                      uint64_t* out_xyz, const affine_t* d_extra, size_t n_extra) {
     if (window_bits < 0 || window_bits > (int)MSM_MAX_WINDOW_BITS) { zk_set_error("msm: window_bits %d outside [0, %u]", window_bits, MSM_MAX_WINDOW_BITS); return ZK_ERR_INVALID; }
     const bool pallas = bases->b.curve == ZK_PALLAS;
     // MSMs per pipeline: the context's limit, and no more than keeps the sorted entry list below 2^28 entries (1 GiB of scratch)
@@ -65,9 +71,9 @@ int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const
         MsmResultShape shape;
         unsigned nl = 0;
         ctx->ws.h_slot = 0;
-        int rc = pallas ? msm_run<FpParams, FqParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl,
+        int rc = pallas ? msm_run<FpParams, FqParams>(bases->b, offs + j0, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl,
                                                       d_extra, n_extra)
-                        : msm_run<FqParams, FpParams>(bases->b, off, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl,
+                        : msm_run<FqParams, FpParams>(bases->b, offs + j0, n, d_scalars + j0, cnt, mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl,
                                                       d_extra, n_extra);
         if (rc) return rc;
         ctx->launches += nl;
@@ -566,8 +572,8 @@ static int msm_partial_impl(zk_ctx* ctx, const zk_bases* bases, size_t off, size
     ctx->ws.d_T_out = (xyzz_t*)d_out;
     ctx->ws.d_T_cap = capacity_points;
     int rc = bases->b.curve == ZK_PALLAS
-                 ? msm_run<FpParams, FqParams>(bases->b, off, n, &d_sc, 1, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl)
-                 : msm_run<FqParams, FpParams>(bases->b, off, n, &d_sc, 1, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
+                 ? msm_run<FpParams, FqParams>(bases->b, &off, n, &d_sc, 1, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl)
+                 : msm_run<FqParams, FpParams>(bases->b, &off, n, &d_sc, 1, scalars_are_mont != 0, (unsigned)window_bits, ctx->ws, ctx->stream, &shape, &nl);
     ctx->ws.d_T_out = nullptr;
     ctx->ws.d_T_cap = 0;
     ctx->launches += nl;

@@ -75,6 +75,9 @@ int ctx_ntt_device_oop(zk_ctx* ctx, int field, const fe* d_in, size_t in_bs, fe*
 // d_extra / n_extra: points of this call only, laid out like the table (msm.cuh); every scalar vector then has n + n_extra entries.
 int ctx_msm_many(zk_ctx* ctx, const zk_bases* bases, size_t off, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
                  uint64_t* out_xyz, const affine_t* d_extra = nullptr, size_t n_extra = 0);
+// the same with one base offset per MSM (the chunks of a chunked Lagrange basis share their scalars, not their bases)
+int ctx_msm_many_offs(zk_ctx* ctx, const zk_bases* bases, const size_t* offs, size_t n, const fe* const* d_scalars, size_t k, int mont, int window_bits,
+                      uint64_t* out_xyz, const affine_t* d_extra = nullptr, size_t n_extra = 0);
 }  // namespace zkb
 
 // host-side mirror of poly_commitment::ipa::SRS<G> (srs.cu); shared with the opening proof (open.cu)

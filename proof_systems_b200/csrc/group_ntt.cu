@@ -8,6 +8,8 @@
 // in global memory, one thread per butterfly  (u, v) -> (u + v, [w^{-j 2^s}] (u - v)),  the twiddle multiplication being a
 // 255-bit double-and-add; then one pass that scales by n^-1, undoes the bit reversal and converts to affine.
 // ~(n/2 log n + n) scalar multiplications: 0.6 M at n = 2^16, tens of milliseconds on a B200 versus tens of seconds on the host.
+#include <algorithm>
+
 #include "msm.cuh"
 
 namespace zkb {
@@ -29,9 +31,13 @@ template <class FS> __global__ void k_gntt_twiddles(fe* tw, fe* ninv, unsigned l
     }
 }
 
-template <class F> __global__ void k_gntt_load(const affine_t* __restrict__ g, xyzz_t* a, unsigned n) {
+// a[start + j] = g[j] for j < terms, the identity elsewhere (one chunk of a chunked basis, ipa.rs:1145-1160; start = 0, terms = n
+// for the plain case)
+template <class F> __global__ void k_gntt_load(const affine_t* __restrict__ g, xyzz_t* a, unsigned n, unsigned start, unsigned terms) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) store_xyzz(a + i, xyzz_from_affine<F>(load_affine_nc(g + i)));
+    if (i >= n) return;
+    const bool live = i >= start && i - start < terms;
+    store_xyzz(a + i, live ? xyzz_from_affine<F>(load_affine_nc(g + (i - start))) : xyzz_identity());
 }
 
 // one DIF layer: half = n >> (s+1); butterfly k: (i0, i1 = i0 + half); twiddle exponent j << s
@@ -58,9 +64,13 @@ template <class F> __global__ void __launch_bounds__(128) k_gntt_finish(const xy
 }
 
 // d_out: n affine points (device).  g: resident generators (row 0 of the table is the points themselves).
-template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigned log_n, affine_t* d_out, cudaStream_t st, unsigned* launches) {
+// Chunk `chunk` of the basis of a domain larger than the SRS (ipa.rs:1145-1171): the inverse FFT of the vector that holds
+// g[0 .. terms) at positions chunk * |g| .. and the identity elsewhere; chunk 0 with n <= |g| is the ordinary basis.
+template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigned log_n, unsigned chunk, affine_t* d_out, cudaStream_t st, unsigned* launches) {
     const unsigned n = 1u << log_n;
-    if (n > g.n) { zk_set_error("lagrange_basis: domain %u larger than the %zu generators (chunked bases are not on the device path)", n, g.n); return ZK_ERR_INVALID; }
+    const size_t start = (size_t)chunk * g.n;
+    if (start >= n && !(chunk == 0 && n <= g.n)) { zk_set_error("lagrange_basis: chunk %u outside a domain of %u over %zu generators", chunk, n, g.n); return ZK_ERR_INVALID; }
+    const unsigned terms = (unsigned)std::min<size_t>(g.n, n - start);
     xyzz_t* a = nullptr;
     fe* tw = nullptr;
     ZK_CUDA(cudaMalloc(&a, (size_t)n * sizeof(xyzz_t)));
@@ -68,7 +78,7 @@ template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigne
     fe* ninv = tw + n / 2 + 1;
     const unsigned ntw = n / 2 ? n / 2 : 1;
     k_gntt_twiddles<FS><<<(ntw + 127) / 128, 128, 0, st>>>(tw, ninv, log_n, ntw);
-    k_gntt_load<F><<<(n + 127) / 128, 128, 0, st>>>(g.d_points, a, n);
+    k_gntt_load<F><<<(n + 127) / 128, 128, 0, st>>>(g.d_points, a, n, (unsigned)start, terms);
     for (unsigned s = 0; s < log_n; s++) k_gntt_layer<F><<<(n / 2 + 127) / 128, 128, 0, st>>>(a, tw, log_n, s);
     k_gntt_finish<F><<<(n + 127) / 128, 128, 0, st>>>(a, ninv, d_out, log_n);
     cudaError_t e = cudaGetLastError();
@@ -80,7 +90,7 @@ template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigne
     return ZK_OK;
 }
 
-template int lagrange_basis_build<FpParams, FqParams>(const MsmBases&, unsigned, affine_t*, cudaStream_t, unsigned*);
-template int lagrange_basis_build<FqParams, FpParams>(const MsmBases&, unsigned, affine_t*, cudaStream_t, unsigned*);
+template int lagrange_basis_build<FpParams, FqParams>(const MsmBases&, unsigned, unsigned, affine_t*, cudaStream_t, unsigned*);
+template int lagrange_basis_build<FqParams, FpParams>(const MsmBases&, unsigned, unsigned, affine_t*, cudaStream_t, unsigned*);
 
 }  // namespace zkb

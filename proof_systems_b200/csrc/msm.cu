@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(1024) k_plan(uint32_t* counts, uint32_t* offse
 }
 
 // Counting-sort scatter: entry (point index | sign) of every non-zero digit goes to its bucket's range.
-__global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned nwin, unsigned batch, unsigned gpm, int per_window, size_t base_off,
+__global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned nwin, unsigned batch, unsigned gpm, int per_window, MsmScalarSet sc,
                           size_t table_stride, int use_table, size_t n_main, size_t n_extra, uint32_t main_count, const uint32_t* offsets,
                           uint32_t* cursors, uint32_t* entries) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,7 +227,7 @@ __global__ void k_scatter(const int32_t* digits, size_t n, unsigned c, unsigned 
     if (sd == 0) return;
     uint32_t pos = offsets[key] + base + (uint32_t)__popc(peers & ((1u << lane) - 1));
     // scalars [0, n_main) belong to the resident bases, [n_main, n) to the call's extra points (their rows behind the table)
-    size_t pidx = i < n_main ? (use_table ? (size_t)w * table_stride : 0) + base_off + i
+    size_t pidx = i < n_main ? (use_table ? (size_t)w * table_stride : 0) + sc.off[in_range ? j : 0] + i
                              : (size_t)main_count + (use_table ? (size_t)w * n_extra : 0) + (i - n_main);
     entries[pos] = (uint32_t)pidx | (sd < 0 ? 0x80000000u : 0u);
 }
@@ -498,11 +498,12 @@ static unsigned pow2_ceil_log(uint64_t x) {
 }
 
 template <class F, class FS>
-int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
+int msm_run(const MsmBases& b, const size_t* offs, size_t n_main, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
             MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches, const affine_t* d_extra, size_t n_extra) {
     const size_t n = n_main + n_extra;                // scalars per MSM
     if (n_extra && !d_extra) { zk_set_error("msm: extra points missing"); return ZK_ERR_INVALID; }
-    if (off > b.n || n_main > b.n - off) { zk_set_error("msm: slice [%zu, %zu) outside the %zu resident bases", off, off + n_main, b.n); return ZK_ERR_INVALID; }
+    for (unsigned j = 0; j < k && j < MSM_MAX_BATCH; j++)
+        if (offs[j] > b.n || n_main > b.n - offs[j]) { zk_set_error("msm: slice [%zu, %zu) outside the %zu resident bases", offs[j], offs[j] + n_main, b.n); return ZK_ERR_INVALID; }
     if (k == 0 || k > MSM_MAX_BATCH) { zk_set_error("msm: batch of %u outside [1, %u]", k, MSM_MAX_BATCH); return ZK_ERR_INVALID; }
     shape->c = 0; shape->groups = 0; shape->batch = k;
     if (n == 0) return ZK_OK;
@@ -610,7 +611,7 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
 #define STAGE_MARK(s) do { if (ws.profile) ZK_CUDA(cudaEventRecord(ws.ev[s], st)); } while (0)
 
     MsmScalarSet sc{};
-    for (unsigned j = 0; j < k; j++) sc.p[j] = d_scalars[j];
+    for (unsigned j = 0; j < k; j++) { sc.p[j] = d_scalars[j]; sc.off[j] = (uint32_t)offs[j]; }
     const uint32_t epoch = ++ws.epoch;
     ZK_CUDA(cudaMemsetAsync(ws.d_counts, 0, NB * sizeof(uint32_t), st));
     ZK_CUDA(cudaMemsetAsync(ws.d_buckets, 0, NB * sizeof(xyzz_t), st));  // all-zero XYZZ == identity
@@ -624,7 +625,7 @@ int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_sca
                                                ws.d_chain_flag, epoch);
     STAGE_MARK(2);
     // 3. scatter (counting sort by bucket)
-    k_scatter<<<(unsigned)((Mmax + 255) / 256), 256, 0, st>>>(ws.d_digits, n, c, nwin, k, gpm, use_table ? 0 : 1, off, b.n, use_table ? 1 : 0,
+    k_scatter<<<(unsigned)((Mmax + 255) / 256), 256, 0, st>>>(ws.d_digits, n, c, nwin, k, gpm, use_table ? 0 : 1, sc, b.n, use_table ? 1 : 0,
                                                             n_main, n_extra, (uint32_t)main_count, ws.d_offsets, ws.d_counts, ws.d_entries);
     STAGE_MARK(3);
     // 4. accumulation: one task per <= K sorted entries of one bucket
@@ -705,7 +706,7 @@ template int msm_sum_partials<FqParams>(const xyzz_t*, size_t, size_t, xyzz_t*, 
 
 #define INST(F, FS)                                                                                                             \
     template int msm_bases_create<F>(MsmBases&, const affine_t*, bool, size_t, unsigned, cudaStream_t);                          \
-    template int msm_run<F, FS>(const MsmBases&, size_t, size_t, const fe* const*, unsigned, bool, unsigned, MsmWorkspace&, cudaStream_t, MsmResultShape*, unsigned*, \
+    template int msm_run<F, FS>(const MsmBases&, const size_t*, size_t, const fe* const*, unsigned, bool, unsigned, MsmWorkspace&, cudaStream_t, MsmResultShape*, unsigned*, \
                                 const affine_t*, size_t);
 INST(FpParams, FqParams)  // Pallas: coordinates Fp, scalars Fq
 INST(FqParams, FpParams)  // Vesta:  coordinates Fq, scalars Fp

@@ -36,6 +36,7 @@ constexpr uint32_t MSM_MAX_GIANTS = 64;       // buckets with > smax tasks get 1
 constexpr unsigned MSM_MAX_BATCH = 16;        // MSMs fused into one pipeline (scalar pointers travel as a kernel parameter)
 struct MsmScalarSet {
     const fe* p[MSM_MAX_BATCH];
+    uint32_t off[MSM_MAX_BATCH];              // first base of MSM j inside the resident set
 };
 
 // A resident set of bases on one device.
@@ -95,7 +96,7 @@ struct MsmResultShape {
     unsigned batch = 0;
 };
 
-// k <= MSM_MAX_BATCH MSMs over bases[off .. off+n) in one pipeline.  d_scalars[j]: the n scalars of MSM j, already on the device
+// k <= MSM_MAX_BATCH MSMs in one pipeline, MSM j over bases[offs[j] .. offs[j]+n).  d_scalars[j]: the n scalars of MSM j, already on the device
 // (8 u32 each).  window c: 0 = default (ignored when the bases carry a precomputed table).  Synchronises the stream (unless
 // ws.defer_sync / ws.d_T_out); the O(c) tail is finished by the caller.
 // d_extra / n_extra: n_extra further points that belong to this call only (h and the fresh base U of an IPA round,
@@ -105,11 +106,11 @@ struct MsmResultShape {
 template <class F> int msm_sum_partials(const xyzz_t* d_all, size_t world, size_t count, xyzz_t* d_out, cudaStream_t st);
 
 template <class F, class FS>
-int msm_run(const MsmBases& b, size_t off, size_t n_main, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
+int msm_run(const MsmBases& b, const size_t* offs, size_t n_main, const fe* const* d_scalars, unsigned k, bool scalars_mont, unsigned c,
             MsmWorkspace& ws, cudaStream_t st, MsmResultShape* shape, unsigned* launches, const affine_t* d_extra = nullptr,
             size_t n_extra = 0);
 
 // group_ntt.cu: Lagrange-basis commitments of the domain of size 2^log_n from the resident generators (SRS::lagrange_basis)
-template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigned log_n, affine_t* d_out, cudaStream_t st, unsigned* launches);
+template <class F, class FS> int lagrange_basis_build(const MsmBases& g, unsigned log_n, unsigned chunk, affine_t* d_out, cudaStream_t st, unsigned* launches);
 
 }  // namespace zkb

@@ -57,16 +57,24 @@ void zk_srs_destroy(zk_srs* srs) {
 
 size_t zk_srs_max_poly_size(const zk_srs* srs) { return srs ? srs->n : 0; }
 
+static size_t basis_chunks(const zk_srs* srs, size_t domain_size) { return (domain_size + srs->n - 1) / srs->n; }   // n.div_ceil(srs_size), ipa.rs:1145
+
 int zk_srs_add_lagrange_basis(zk_srs* srs, size_t domain_size, const uint64_t* basis_xy, int window_bits) {
     if (!srs || !basis_xy || domain_size == 0) { zk_set_error("add_lagrange_basis: null/empty argument"); return ZK_ERR_INVALID; }
-    if (domain_size > srs->n) { zk_set_error("add_lagrange_basis: chunked bases (domain %zu > srs %zu) are not on the device path yet", domain_size, srs->n); return ZK_ERR_INVALID; }
+    // a domain larger than the SRS has ceil(domain / |g|) chunks per element (ipa.rs:1145-1171): basis_xy is chunk-major,
+    // chunk c's domain_size points at basis_xy + 8 * c * domain_size
+    const size_t chunks = basis_chunks(srs, domain_size);
     zk_bases* b = nullptr;
-    int rc = zk_bases_upload(srs->ctx, srs->curve, basis_xy, domain_size, window_bits, 0, &b);
+    int rc = zk_bases_upload(srs->ctx, srs->curve, basis_xy, domain_size * chunks, window_bits, 0, &b);
     if (rc) return rc;
     auto it = srs->lagrange.find(domain_size);
     if (it != srs->lagrange.end()) { zk_bases_free(it->second); it->second = b; }
     else srs->lagrange.emplace(domain_size, b);
     return ZK_OK;
+}
+
+size_t zk_srs_lagrange_basis_chunks(const zk_srs* srs, size_t domain_size) {
+    return srs && domain_size ? basis_chunks(srs, domain_size) : 0;
 }
 
 // SRS::get_lagrange_basis_from_domain_size (ipa.rs:780-788) -> SRS::lagrange_basis (ipa.rs:1065-1172), on the device:
@@ -75,24 +83,26 @@ int zk_srs_add_lagrange_basis(zk_srs* srs, size_t domain_size, const uint64_t* b
 int zk_srs_lagrange_basis(zk_srs* srs, size_t domain_size, int window_bits) {
     if (!srs || domain_size == 0 || (domain_size & (domain_size - 1))) { zk_set_error("lagrange_basis: domain size must be a power of two"); return ZK_ERR_INVALID; }
     if (srs->lagrange.count(domain_size)) return ZK_OK;
-    if (domain_size > srs->n) { zk_set_error("lagrange_basis: chunked bases (domain %zu > srs %zu) are not on the device path yet", domain_size, srs->n); return ZK_ERR_INVALID; }
+    if (domain_size > ((size_t)1 << 30)) { zk_set_error("lagrange_basis: domain %zu too large", domain_size); return ZK_ERR_INVALID; }
     unsigned log_n = 0;
     while (((size_t)1 << log_n) < domain_size) log_n++;
+    const size_t chunks = basis_chunks(srs, domain_size);
     zk_ctx* ctx = srs->ctx;
     affine_t* d_out = nullptr;
-    int rc;
+    int rc = ZK_OK;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         ZK_CUDA(cudaSetDevice(ctx->device));
-        ZK_CUDA(cudaMalloc(&d_out, domain_size * sizeof(affine_t)));
+        ZK_CUDA(cudaMalloc(&d_out, chunks * domain_size * sizeof(affine_t)));
         unsigned nl = 0;
-        rc = srs->curve == ZK_PALLAS ? lagrange_basis_build<FpParams, FqParams>(srs->g->b, log_n, d_out, ctx->stream, &nl)
-                                     : lagrange_basis_build<FqParams, FpParams>(srs->g->b, log_n, d_out, ctx->stream, &nl);
+        for (size_t c = 0; c < chunks && rc == ZK_OK; c++)
+            rc = srs->curve == ZK_PALLAS ? lagrange_basis_build<FpParams, FqParams>(srs->g->b, log_n, (unsigned)c, d_out + c * domain_size, ctx->stream, &nl)
+                                         : lagrange_basis_build<FqParams, FpParams>(srs->g->b, log_n, (unsigned)c, d_out + c * domain_size, ctx->stream, &nl);
         ctx->launches += nl;
     }
     if (rc == ZK_OK) {
         zk_bases* b = nullptr;
-        rc = zk_bases_upload(ctx, srs->curve, (const uint64_t*)d_out, domain_size, window_bits, /*points_on_device=*/1, &b);
+        rc = zk_bases_upload(ctx, srs->curve, (const uint64_t*)d_out, chunks * domain_size, window_bits, /*points_on_device=*/1, &b);
         if (rc == ZK_OK) srs->lagrange.emplace(domain_size, b);
     }
     cudaFree(d_out);
@@ -104,10 +114,11 @@ int zk_srs_get_lagrange_basis(zk_srs* srs, size_t domain_size, uint64_t* out_xy,
     if (!srs || !out_xy) { zk_set_error("get_lagrange_basis: null argument"); return ZK_ERR_INVALID; }
     auto it = srs->lagrange.find(domain_size);
     if (it == srs->lagrange.end()) { zk_set_error("get_lagrange_basis: no basis for domain size %zu", domain_size); return ZK_ERR_INVALID; }
-    if (capacity_points < domain_size) { zk_set_error("get_lagrange_basis: capacity %zu < %zu", capacity_points, domain_size); return ZK_ERR_INVALID; }
+    const size_t total = domain_size * basis_chunks(srs, domain_size);     // chunk-major
+    if (capacity_points < total) { zk_set_error("get_lagrange_basis: capacity %zu < %zu", capacity_points, total); return ZK_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(srs->ctx->mu);
     ZK_CUDA(cudaSetDevice(srs->ctx->device));
-    ZK_CUDA(cudaMemcpy(out_xy, it->second->b.d_points, domain_size * sizeof(affine_t), cudaMemcpyDeviceToHost));
+    ZK_CUDA(cudaMemcpy(out_xy, it->second->b.d_points, total * sizeof(affine_t), cudaMemcpyDeviceToHost));
     return ZK_OK;
 }
 
@@ -167,10 +178,22 @@ int zk_srs_commit_evaluations_non_hiding(zk_srs* srs, size_t domain_size, const 
         for (size_t i = 0; i < domain_size; i++) memcpy(&sub[4 * i], evals_mont + 4 * s * i, 32);
         sc = sub.data();
     }
-    uint64_t jac[12];
-    int rc = zk_msm(srs->ctx, it->second, 0, domain_size, sc, /*mont=*/1, 0, jac);
-    if (rc) return rc;
-    return zk_jacobian_to_affine(srs->curve, jac, out_xy);
+    // PolyComm::multi_scalar_mul (commitment.rs:350-394): one MSM per chunk of the basis elements, all with the same scalars
+    const size_t chunks = basis_chunks(srs, domain_size);
+    if (chunks == 1) {
+        uint64_t jac[12];
+        int rc = zk_msm(srs->ctx, it->second, 0, domain_size, sc, /*mont=*/1, 0, jac);
+        if (rc) return rc;
+        return zk_jacobian_to_affine(srs->curve, jac, out_xy);
+    }
+    for (size_t c = 0; c < chunks; c++) {
+        uint64_t jac[12];
+        int rc = zk_msm(srs->ctx, it->second, c * domain_size, domain_size, sc, /*mont=*/1, 0, jac);
+        if (rc) return rc;
+        rc = zk_jacobian_to_affine(srs->curve, jac, out_xy + 8 * c);
+        if (rc) return rc;
+    }
+    return ZK_OK;
 }
 
 // k independent commit_evaluations_non_hiding calls on the same domain (the reference issues the 15 witness columns from
@@ -179,6 +202,7 @@ int zk_srs_commit_evaluations_batch(zk_srs* srs, size_t domain_size, const uint6
     if (!srs || (!evals_mont && k) || (!out_xy && k)) { zk_set_error("commit_evaluations_batch: null argument"); return ZK_ERR_INVALID; }
     auto it = srs->lagrange.find(domain_size);
     if (it == srs->lagrange.end()) { zk_set_error("commit_evaluations: no Lagrange basis registered for domain size %zu", domain_size); return ZK_ERR_INVALID; }
+    if (basis_chunks(srs, domain_size) != 1) { zk_set_error("commit_evaluations_batch: chunked bases (domain %zu > srs %zu) go through zk_srs_commit_evaluations_non_hiding", domain_size, srs->n); return ZK_ERR_INVALID; }
     std::vector<uint64_t> jac(12 * k);
     int rc = zk_msm_batch(srs->ctx, it->second, 0, domain_size, evals_mont, k, /*mont=*/1, 0, jac.data());
     if (rc) return rc;

@@ -77,16 +77,22 @@ class SRS:
     def add_lagrange_basis(self, domain_size: int, basis, window_bits: int = -1):
         """Populate the cache behind get_lagrange_basis(domain) (ipa.rs:780-795) with a precomputed basis."""
         b = _np_u64(basis, (8,))
-        assert b.shape[0] == domain_size
+        assert b.shape[0] == domain_size * self.lagrange_basis_chunks(domain_size)      # chunk-major for domains larger than the SRS
         check(lib().zk_srs_add_lagrange_basis(self._h, domain_size, _ptr(b), window_bits))
+
+    def lagrange_basis_chunks(self, domain_size: int) -> int:
+        """chunks per basis element: ceil(domain / |g|) (ipa.rs:1145)"""
+        return int(lib().zk_srs_lagrange_basis_chunks(self._h, domain_size))
 
     # fn get_lagrange_basis_from_domain_size(&self, domain_size: usize) -> &Vec<PolyComm<G>>
     def get_lagrange_basis_from_domain_size(self, domain_size: int, window_bits: int = -1) -> np.ndarray:
-        """Computes (once) the basis on the device — SRS::lagrange_basis, ipa.rs:1065-1172 — and returns it: [n, 8] affine."""
+        """Computes (once) the basis on the device — SRS::lagrange_basis, ipa.rs:1065-1172 — and returns it: [n, 8] affine, or
+        [chunks, n, 8] (chunk-major: PolyComm i of the reference is out[:, i]) when the domain is larger than the SRS."""
         check(lib().zk_srs_lagrange_basis(self._h, domain_size, window_bits))
-        out = np.empty((domain_size, 8), dtype=np.uint64)
-        check(lib().zk_srs_get_lagrange_basis(self._h, domain_size, out.ctypes.data_as(_u64p), domain_size))
-        return out
+        chunks = self.lagrange_basis_chunks(domain_size)
+        out = np.empty((chunks * domain_size, 8), dtype=np.uint64)
+        check(lib().zk_srs_get_lagrange_basis(self._h, domain_size, out.ctypes.data_as(_u64p), chunks * domain_size))
+        return out if chunks == 1 else out.reshape(chunks, domain_size, 8)
 
     # fn commit_non_hiding(&self, plnm: &DensePolynomial<F>, num_chunks: usize) -> PolyComm<G>
     def commit_non_hiding(self, coeffs, num_chunks: int) -> PolyComm:
@@ -101,7 +107,7 @@ class SRS:
     # fn commit_evaluations_non_hiding(&self, domain: D<F>, plnm: &Evaluations<F, D<F>>) -> PolyComm<G>
     def commit_evaluations_non_hiding(self, domain_size: int, evals) -> PolyComm:
         e = _np_u64(evals, (4,))
-        out = np.zeros((1, 8), dtype=np.uint64)
+        out = np.zeros((max(1, self.lagrange_basis_chunks(domain_size)), 8), dtype=np.uint64)
         check(lib().zk_srs_commit_evaluations_non_hiding(self._h, domain_size, _ptr(e), e.shape[0], out.ctypes.data_as(_u64p)))
         return PolyComm(out)
 

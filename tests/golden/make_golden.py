@@ -18,9 +18,8 @@ Outputs (tests/golden/):
                   lag_2048   uint8 [2048,64]   lagrange_bases[2048][i] for all i  (config 1: 2048 pinned 2^11-point MSMs)
                   lag_small  uint8 [2047,64]   lagrange_bases[n][i], n = 1,2,..,1024 concatenated
                   lag_65536_idx int64 [k], lag_65536 uint8 [k,64]   sampled answers of 2^16-point MSMs
-  vesta_srs.npz   g_cmp      uint8 [2048,33], g_xy, h_xy, lag_2048, lag_small, lag_65536_idx, lag_65536
-                  (Vesta keeps only the first 2048 generators; lag_65536 therefore cannot be re-derived from the
-                   fixture alone and is kept for the container-side check only.)
+                  lag_65536_sha256 uint8 [32]   sha256 of the whole stored 2^16 basis (65536 x 64 canonical bytes, index order)
+  vesta_srs.npz   the same keys
 """
 import os
 import sys
@@ -50,7 +49,7 @@ def main():
         g_c, h_c = small
         g_u, h_u, lag = test
         assert len(g_c) == 65536 and len(g_u) == 65536
-        keep = 65536 if curve == "pallas" else 2048
+        keep = 65536          # both curves keep every generator since round 2: the 2^16 prover replay (tests/test_gpu_replay.py) commits on Vesta
         g_cmp = np.stack([np.frombuffer(p, dtype=np.uint8) for p in g_c[:keep]])
         g_xy = np.stack([xy(p) for p in g_u[:2048]])
         # the two files agree on x for every generator
@@ -60,6 +59,9 @@ def main():
         lag_small = np.concatenate([np.stack([xy(c[0]) for c in lag[1 << k]]) for k in range(11)])
         assert lag_small.shape == (2047, 64)
         lag_65536 = np.stack([xy(lag[65536][i][0]) for i in SAMPLE_65536])
+        # the WHOLE stored 2^16 basis, pinned by digest: 65536 x (x || y), canonical LE, in index order
+        import hashlib
+        digest = hashlib.sha256(b"".join(bytes(lag[65536][i][0][:64]) for i in range(65536))).digest()
         np.savez(
             os.path.join(OUT, f"{curve}_srs.npz"),
             g_cmp=g_cmp,
@@ -69,6 +71,7 @@ def main():
             lag_small=lag_small,
             lag_65536_idx=np.array(SAMPLE_65536, dtype=np.int64),
             lag_65536=lag_65536,
+            lag_65536_sha256=np.frombuffer(digest, dtype=np.uint8),
         )
         print(curve, "ok", os.path.getsize(os.path.join(OUT, f"{curve}_srs.npz")))
 

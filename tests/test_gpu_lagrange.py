@@ -44,3 +44,32 @@ def test_lagrange_basis_2_16_sampled(ctx, orc, pallas_srs):
         assert np.array_equal(basis[int(i)], want[k]), int(i)
     assert all(orc.on_curve(g.cid, basis[i]) for i in range(0, 1 << 16, 4099))
     srs.close()
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_chunked_lagrange_basis_and_commitment(ctx, orc, request, name):
+    """A domain larger than the SRS (poly-commitment/src/ipa.rs:1145-1171): chunk c of element i is
+    sum_j (w^{-i (c |g| + j)} / n) g[j] over the chunk's terms — every entry checked against that MSM on the oracle — and
+    commit_evaluations_non_hiding returns one point per chunk, each the MSM of the evaluations against that chunk of the basis
+    (PolyComm::multi_scalar_mul, commitment.rs:350-394), equal to committing the interpolated polynomial chunk by chunk."""
+    G = request.getfixturevalue(name)
+    srs_len, n = 24, 64                                  # 3 chunks: 24 + 24 + 16 terms
+    srs = zk.SRS(ctx, G.cid, G.g[:srs_len], G.mont_points(G.h_xy_canon)[0])
+    assert srs.lagrange_basis_chunks(n) == 3 and srs.lagrange_basis_chunks(16) == 1
+    basis = srs.get_lagrange_basis_from_domain_size(n)
+    assert basis.shape == (3, n, 8)
+    m = orc.MODULUS[G.scalar]
+    w = orc.fe_int(G.scalar, orc.root_of_unity(G.scalar, 6))
+    winv, ninv = pow(w, -1, m), pow(n, -1, m)
+    for c in range(3):
+        terms = min(srs_len, n - c * srs_len)
+        for i in (0, 1, 17, 63):
+            scal = [pow(winv, i * (c * srs_len + j), m) * ninv % m for j in range(terms)]
+            assert np.array_equal(basis[c, i], orc.msm(G.cid, G.g[:terms], orc.ints_to_limbs(scal))), (c, i)
+    evals = orc.to_mont(G.scalar, orc.random_scalars(G.scalar, n, seed=44))
+    com = srs.commit_evaluations_non_hiding(n, evals)
+    assert len(com) == 3
+    coeffs = orc.ntt(G.scalar, evals, inverse=True)
+    via_coeffs = srs.commit_non_hiding(coeffs, 1)        # 64 coefficients over |g| = 24: the same three chunks
+    assert np.array_equal(com.chunks, via_coeffs.chunks)
+    srs.close()
