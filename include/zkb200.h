@@ -271,14 +271,36 @@ int zk_srs_open(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, const ui
  * device — kimchi/src/circuits/polynomials/permutation.rs:223-357, `perm`:
  *   out[i] = alpha0 * zkpm[i] * ( z[i] * prod_{k<7} (w_k[i] + gamma + beta * shift_k * x_i)
  *                               - z[(i + next_shift) mod m] * prod_{k<7} (w_k[i] + gamma + beta * sigma_k[i]) ),     x_i = omega_m^i
- * d_w: the 7 permuted witness columns over d8, column k at d_w + k * w_stride elements (the output of zk_ntt_dev_oop on the
- * interpolated columns); d_sigma: permutation_coefficients8 likewise; d_z: z over d8; d_zkpm: permutation_vanishing_polynomial_l
+ * d_w[k]: the 7 permuted witness columns over d8 (the output of zk_ntt_dev_oop on the interpolated columns); d_sigma[k]:
+ * permutation_coefficients8 (e.g. the sections of a cached prover index, zk_index_cache_section); d_z: z over d8; d_zkpm:
+ * permutation_vanishing_polynomial_l
  * over d8; next_shift = m / n = 8 (z(x omega) is z shifted by eight positions of d8, constraints.rs:497-505); beta, gamma, alpha0
  * and the 7 shifts (cs.shift) are Montgomery scalars passed by value. */
-int zk_perm_quotient_dev(zk_ctx* ctx, int field_id, unsigned log_m, const void* d_w, size_t w_stride, const void* d_z,
-                         const void* d_sigma, size_t sigma_stride, const void* d_zkpm, const uint64_t beta[4],
-                         const uint64_t gamma[4], const uint64_t alpha0[4], const uint64_t shifts[28], unsigned next_shift,
-                         void* d_out);
+int zk_perm_quotient_dev(zk_ctx* ctx, int field_id, unsigned log_m, const void* const d_w[7], const void* d_z,
+                         const void* const d_sigma[7], const void* d_zkpm, const uint64_t beta[4], const uint64_t gamma[4],
+                         const uint64_t alpha0[4], const uint64_t shifts[28], unsigned next_shift, void* d_out);
+
+/* ------------------------------------------------------------------ cached prover index
+ * Device-side ingestion of kimchi's mmap-backed proving-key cache, kimchi/src/cached_prover_index.rs:26-56 ("MINAPK01", format 3):
+ * the file stores the index's big arrays — coefficients8 (15 columns), permutation_coefficients8 (7), the gate selectors over d4 / d8,
+ * sid, the lookup tables — as raw Montgomery limbs, which is the device format, so the payload is copied to the device AS IT LIES in
+ * the mapping (one copy, no per-element decoding) and then serves as resident operands (zk_perm_quotient_dev, zk_msm_dev ...).
+ * image: the file's bytes (e.g. the mmap); expect_identifier: NULL or the identifier the file must carry (IdentifierMismatch).
+ * Section tags are the reference's SectionTag values: 0x01 sid, 0x10 + i coefficients8[i], 0x20..0x25 selectors,
+ * 0x30 + i permutation_coefficients8[i], 0x40..0x45 optional selectors, 0x50..0x56 lookup arrays. */
+typedef struct zk_index_cache zk_index_cache;
+typedef struct zk_index_header {      /* ScalarHeader + preamble fields, cached_prover_index.rs:173-225 */
+    uint32_t public_inputs, prev_challenges;
+    uint64_t zk_rows, max_poly_size, domain_d1_size;
+    uint32_t feature_flags, optional_selectors_present, lookup_selectors_present, num_sections;
+    int disable_gates_checks, has_verifier_index_digest;
+    uint64_t endo[4], shift[7][4], verifier_index_digest[4];   /* Montgomery limbs */
+    char identifier[512];
+} zk_index_header;
+int zk_index_cache_load(zk_ctx* ctx, const void* image, size_t image_len, const char* expect_identifier, zk_index_cache** out);
+void zk_index_cache_free(zk_index_cache* cache);
+int zk_index_cache_header(const zk_index_cache* cache, zk_index_header* out);
+int zk_index_cache_section(const zk_index_cache* cache, uint32_t tag, const void** d_ptr, size_t* n_elems, uint32_t* elem_domain_size);
 
 /* ------------------------------------------------------------------ diagnostics (tests/test_gpu_field.py, DESIGN.md compute model)
  * Element-wise device field ops on n elements (op: 0 mul, 1 add, 2 sub, 3 inverse of a), host pointers. */

@@ -107,7 +107,12 @@ def lib() -> ctypes.CDLL:
     L.zk_dev_free.argtypes = [vp, vp]
     L.zk_dev_upload.argtypes = [vp, vp, vp, sz]
     L.zk_dev_download.argtypes = [vp, vp, vp, sz]
-    L.zk_perm_quotient_dev.argtypes = [vp, i, u, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp, u, vp]
+    L.zk_perm_quotient_dev.argtypes = [vp, i, u, vp, vp, vp, vp, vp, vp, vp, vp, u, vp]
+    L.zk_index_cache_load.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.zk_index_cache_free.argtypes = [vp]
+    L.zk_index_cache_free.restype = None
+    L.zk_index_cache_header.argtypes = [vp, ctypes.POINTER(IndexHeader)]
+    L.zk_index_cache_section.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_uint32)]
     L.zk_comm_unique_id.argtypes = [vp]
     L.zk_comm_init_rank.argtypes = [vp, vp, i, i, ctypes.POINTER(vp)]
     L.zk_comm_destroy.argtypes = [vp]
@@ -116,6 +121,15 @@ def lib() -> ctypes.CDLL:
     L.zk_srs_open.argtypes = [vp, ctypes.POINTER(OpenPoly), sz, vp, sz, vp, vp, vp, sz, ctypes.POINTER(OpenTranscript), vp, sz,
                               ctypes.POINTER(sz), vp, vp, vp, vp]
     return L
+
+
+class IndexHeader(ctypes.Structure):
+    """zk_index_header (include/zkb200.h)"""
+    _fields_ = [("public_inputs", ctypes.c_uint32), ("prev_challenges", ctypes.c_uint32), ("zk_rows", ctypes.c_uint64), ("max_poly_size", ctypes.c_uint64),
+                ("domain_d1_size", ctypes.c_uint64), ("feature_flags", ctypes.c_uint32), ("optional_selectors_present", ctypes.c_uint32),
+                ("lookup_selectors_present", ctypes.c_uint32), ("num_sections", ctypes.c_uint32), ("disable_gates_checks", ctypes.c_int),
+                ("has_verifier_index_digest", ctypes.c_int), ("endo", ctypes.c_uint64 * 4), ("shift", (ctypes.c_uint64 * 4) * 7),
+                ("verifier_index_digest", ctypes.c_uint64 * 4), ("identifier", ctypes.c_char * 512)]
 
 
 class OpenPoly(ctypes.Structure):
@@ -326,13 +340,15 @@ class Context:
         check(lib().zk_dev_download(self._h, _ptr(out), ctypes.c_void_p(d_src), out.nbytes))
         return out
 
-    def perm_quotient_dev(self, field: int, log_m: int, d_w: int, w_stride: int, d_z: int, d_sigma: int, sigma_stride: int, d_zkpm: int, beta, gamma,
-                          alpha0, shifts, d_out: int, next_shift: int = 8):
-        """zk_perm_quotient_dev: the permutation part of the quotient over d8, operands resident on the device"""
+    def perm_quotient_dev(self, field: int, log_m: int, d_w, d_z: int, d_sigma, d_zkpm: int, beta, gamma, alpha0, shifts, d_out: int, next_shift: int = 8):
+        """zk_perm_quotient_dev: the permutation part of the quotient over d8, operands resident on the device; d_w, d_sigma: 7 device
+        pointers each"""
         c = lambda a, k: np.ascontiguousarray(a, dtype=np.uint64).reshape(k)
         b, g, a0, sh = c(beta, 4), c(gamma, 4), c(alpha0, 4), c(shifts, 28)
-        check(lib().zk_perm_quotient_dev(self._h, field, log_m, ctypes.c_void_p(d_w), w_stride, ctypes.c_void_p(d_z), ctypes.c_void_p(d_sigma), sigma_stride,
-                                         ctypes.c_void_p(d_zkpm), _ptr(b), _ptr(g), _ptr(a0), _ptr(sh), next_shift, ctypes.c_void_p(d_out)))
+        pw = (ctypes.c_void_p * 7)(*[int(p) for p in d_w])
+        ps = (ctypes.c_void_p * 7)(*[int(p) for p in d_sigma])
+        check(lib().zk_perm_quotient_dev(self._h, field, log_m, pw, ctypes.c_void_p(d_z), ps, ctypes.c_void_p(d_zkpm), _ptr(b), _ptr(g), _ptr(a0), _ptr(sh),
+                                         next_shift, ctypes.c_void_p(d_out)))
 
     # ------------------------------------------------------------------ diagnostics
     def field_op(self, field: int, op: str, a, b=None) -> np.ndarray:

@@ -221,12 +221,14 @@ int ctx_acquire_lane(zk_ctx* ctx, LaneLock& out) {
         lanes.insert(lanes.end(), ctx->children.begin(), ctx->children.end());
         start = ctx->rr++;
     }
-    for (size_t k = 0; k < lanes.size(); k++) {
-        zk_ctx* l = lanes[(start + k) % lanes.size()];
+    // the primary lane first, then the children in order: a single-threaded caller always lands on the same (warm) lane, only
+    // contention spills over; when every lane is busy the waiters spread round-robin
+    for (size_t k = 0; k < lanes.size() && k < (size_t)ctx->n_lanes; k++) {
+        zk_ctx* l = lanes[k];
         std::unique_lock<std::mutex> lk(l->mu, std::try_to_lock);
         if (lk.owns_lock()) { out.lane = l; out.lk = std::move(lk); return ZK_OK; }
     }
-    zk_ctx* l = lanes[start % lanes.size()];
+    zk_ctx* l = lanes[start % std::min<size_t>(lanes.size(), (size_t)ctx->n_lanes)];
     out.lane = l;
     out.lk = std::unique_lock<std::mutex>(l->mu);
     return ZK_OK;

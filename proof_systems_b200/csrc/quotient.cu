@@ -19,15 +19,15 @@ using namespace zkb;
 namespace zkb {
 
 struct PermQuotArgs {
-    const fe* w;        // [7][w_stride]
-    const fe* sigma;    // [7][sigma_stride]
+    const fe* w[7];     // the 7 permuted witness columns over d8
+    const fe* sigma[7]; // permutation_coefficients8
     const fe* z;
     const fe* zkpm;
     const fe* ulo;      // x_i = omega_m^i from the forward transform's tables (ntt.cuh): ulo[i & 1023] * mid[(i >> 10) & 1023] * hi2[i >> 20]
     const fe* mid;
     const fe* hi2;
     fe* out;
-    size_t w_stride, sigma_stride, m;
+    size_t m;
     unsigned next_shift;
     fe beta, gamma, alpha0;
     fe shift[7];
@@ -45,9 +45,9 @@ template <class FS> __global__ void __launch_bounds__(128) k_perm_quotient(const
     fe shifts = load_fe_nc(a.z + i), sigmas = load_fe_nc(a.z + inext);
 #pragma unroll 1
     for (unsigned k = 0; k < 7; k++) {
-        const fe wg = fe_add<FS>(load_fe_nc(a.w + k * a.w_stride + i), a.gamma);
+        const fe wg = fe_add<FS>(load_fe_nc(a.w[k] + i), a.gamma);
         shifts = fe_mul<FS>(shifts, fe_add<FS>(wg, fe_mul<FS>(bx, a.shift[k])));
-        sigmas = fe_mul<FS>(sigmas, fe_add<FS>(wg, fe_mul<FS>(a.beta, load_fe_nc(a.sigma + k * a.sigma_stride + i))));
+        sigmas = fe_mul<FS>(sigmas, fe_add<FS>(wg, fe_mul<FS>(a.beta, load_fe_nc(a.sigma[k] + i))));
     }
     const fe r = fe_mul<FS>(fe_mul<FS>(fe_sub<FS>(shifts, sigmas), a.alpha0), load_fe_nc(a.zkpm + i));
     store_fe(a.out + i, r);
@@ -57,21 +57,24 @@ int ctx_ntt_table_ptrs(zk_ctx* ctx, int field, unsigned log_n, bool inverse, con
 
 }  // namespace zkb
 
-extern "C" int zk_perm_quotient_dev(zk_ctx* ctx, int field_id, unsigned log_m, const void* d_w, size_t w_stride, const void* d_z, const void* d_sigma,
-                                    size_t sigma_stride, const void* d_zkpm, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha0[4],
+extern "C" int zk_perm_quotient_dev(zk_ctx* ctx, int field_id, unsigned log_m, const void* const d_w[7], const void* d_z, const void* const d_sigma[7],
+                                    const void* d_zkpm, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t alpha0[4],
                                     const uint64_t shifts[28], unsigned next_shift, void* d_out) {
     if (!ctx || !d_w || !d_z || !d_sigma || !d_zkpm || !beta || !gamma || !alpha0 || !shifts || !d_out) { zk_set_error("perm_quotient: null argument"); return ZK_ERR_INVALID; }
     if (field_id != ZK_FP && field_id != ZK_FQ) { zk_set_error("perm_quotient: unknown field_id %d", field_id); return ZK_ERR_INVALID; }
     if (log_m > 30) { zk_set_error("perm_quotient: log_m %u > 30", log_m); return ZK_ERR_INVALID; }
     const size_t m = (size_t)1 << log_m;
-    if (w_stride < m || sigma_stride < m || next_shift >= m) { zk_set_error("perm_quotient: strides / shift do not fit a domain of %zu", m); return ZK_ERR_INVALID; }
+    if (next_shift >= m) { zk_set_error("perm_quotient: shift %u does not fit a domain of %zu", next_shift, m); return ZK_ERR_INVALID; }
+    for (int k = 0; k < 7; k++)
+        if (!d_w[k] || !d_sigma[k]) { zk_set_error("perm_quotient: column %d is null", k); return ZK_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ZK_CUDA(cudaSetDevice(ctx->device));
     PermQuotArgs a{};
     int rc = ctx_ntt_table_ptrs(ctx, field_id, log_m, false, &a.ulo, &a.mid, &a.hi2);
     if (rc) return rc;
-    a.w = (const fe*)d_w; a.sigma = (const fe*)d_sigma; a.z = (const fe*)d_z; a.zkpm = (const fe*)d_zkpm; a.out = (fe*)d_out;
-    a.w_stride = w_stride; a.sigma_stride = sigma_stride; a.m = m; a.next_shift = next_shift;
+    for (int k = 0; k < 7; k++) { a.w[k] = (const fe*)d_w[k]; a.sigma[k] = (const fe*)d_sigma[k]; }
+    a.z = (const fe*)d_z; a.zkpm = (const fe*)d_zkpm; a.out = (fe*)d_out;
+    a.m = m; a.next_shift = next_shift;
     memcpy(&a.beta, beta, 32); memcpy(&a.gamma, gamma, 32); memcpy(&a.alpha0, alpha0, 32);
     memcpy(a.shift, shifts, 7 * 32);
     const unsigned blocks = (unsigned)((m + 127) / 128);

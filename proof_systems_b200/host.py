@@ -140,6 +140,47 @@ class SRS:
         return self.mask_custom(self.commit_evaluations_non_hiding(domain_size, evals), blinders)
 
 
+class IndexCache:
+    """A cached prover index (kimchi/src/cached_prover_index.rs:26-56, "MINAPK01") resident on the device: zk_index_cache_load parses the
+    header and the section table and copies the payload as it lies in the file — raw Montgomery limbs are the device format."""
+
+    def __init__(self, ctx: Context, image: bytes, expect_identifier: str | None = None):
+        from ._lib import IndexHeader
+        self.ctx = ctx
+        self._image = np.frombuffer(image, dtype=np.uint8)          # keeps the bytes alive during the copy
+        self._h = ctypes.c_void_p()
+        ident = expect_identifier.encode() if expect_identifier is not None else None
+        check(lib().zk_index_cache_load(ctx._h, ctypes.c_void_p(self._image.ctypes.data), self._image.size, ident, ctypes.byref(self._h)))
+        hdr = IndexHeader()
+        check(lib().zk_index_cache_header(self._h, ctypes.byref(hdr)))
+        self.header = hdr
+
+    @classmethod
+    def from_file(cls, ctx: Context, path: str, expect_identifier: str | None = None) -> "IndexCache":
+        import mmap
+        with open(path, "rb") as f:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        return cls(ctx, mm, expect_identifier)
+
+    def section(self, tag: int):
+        """(device pointer, element count, declared domain size) of a field-element section"""
+        p, n, d = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_uint32()
+        check(lib().zk_index_cache_section(self._h, tag, ctypes.byref(p), ctypes.byref(n), ctypes.byref(d)))
+        return p.value or 0, n.value, d.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zk_index_cache_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
 class OpeningProof:
     """poly_commitment::ipa::OpeningProof (ipa.rs:1175-1191): lr [rounds, 2, 8], delta [8], z1 [4], z2 [4], sg [8] — points affine,
     everything in Montgomery limbs"""

@@ -29,7 +29,8 @@ def test_permutation_quotient_kernel_vs_oracle(ctx, orc, fid, log_m):
     try:
         for k, v in (("w", w), ("sigma", sigma), ("z", z), ("zkpm", zkpm)):
             ctx.dev_upload(bufs[k], v)
-        ctx.perm_quotient_dev(fid, log_m, bufs["w"], m, bufs["z"], bufs["sigma"], m, bufs["zkpm"], beta, gamma, alpha0, shifts, bufs["out"])
+        cols = lambda base: [base + k * m * 32 for k in range(7)]
+        ctx.perm_quotient_dev(fid, log_m, cols(bufs["w"]), bufs["z"], cols(bufs["sigma"]), bufs["zkpm"], beta, gamma, alpha0, shifts, bufs["out"])
         assert np.array_equal(ctx.dev_download(bufs["out"], (m, 4)), want)
     finally:
         for p in bufs.values():
@@ -66,7 +67,8 @@ def test_device_resident_d8_pipeline(ctx, orc):
         ctx.dev_upload(d_zkpm, zkpm)
         ctx.ntt_dev(fid, d_cols, log_n, batch=8, inverse=True)                 # prover.rs:370-381
         ctx.ntt_dev_oop(fid, d_cols, n, n, d_ev8, log_n + 3, batch=8)           # constraints.rs:488-507
-        ctx.perm_quotient_dev(fid, log_n + 3, d_ev8, m, d_ev8 + 7 * m * 32, d_sigma, m, d_zkpm, beta, gamma, alpha0, shifts, d_out)
+        ctx.perm_quotient_dev(fid, log_n + 3, [d_ev8 + k * m * 32 for k in range(7)], d_ev8 + 7 * m * 32, [d_sigma + k * m * 32 for k in range(7)], d_zkpm,
+                              beta, gamma, alpha0, shifts, d_out)
         ctx.ntt_dev(fid, d_out, log_n + 3, inverse=True)                        # prover.rs:907
         got = ctx.dev_download(d_out, (m, 4))
         assert np.array_equal(got, want)
