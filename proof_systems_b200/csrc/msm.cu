@@ -275,6 +275,87 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
     store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
 }
 
+// ---------------------------------------------------------------------------------------------- accumulation, TMA-staged gather
+// The same accumulation with the gather moved to the bulk asynchronous copy engine (TMA, `cp.async.bulk`; UBLKCP in SASS): every lane
+// asks the copy engine for its next 64-byte point, to be dropped in its own shared-memory slot and signalled on the warp's mbarrier,
+// while it adds the current one — two stages per lane.  BASELINE's north star names this staging; on this kernel it is measured,
+// not assumed (zk_ctx_set_option "msm_tma", tools/msm_tma_ab.py, profiles/r02_tma_ab.md): the kernel is bound by the FMA-heavy pipe
+// (74.9 % busy, LSU 0.7 %), so taking the loads off the LSU path buys nothing and the shared-memory round trip costs a little.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate_tma(const affine_t* __restrict__ points, const uint32_t* __restrict__ entries,
+                                                        const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
+                                                        uint32_t K, const uint32_t* __restrict__ meta, const affine_t* __restrict__ extra,
+                                                        uint32_t main_count, xyzz_t* buckets, xyzz_t* partials) {
+    __shared__ alignas(128) affine_t slots[2][128];
+    __shared__ alignas(8) uint64_t bars[2][4];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t t = blockIdx.x * blockDim.x + tid;
+    if (lane == 0) { mbar_init(smem_u32(&bars[0][warp]), 32); mbar_init(smem_u32(&bars[1][warp]), 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const bool live = t < __ldg(meta + 1);
+    uint32_t b = 0, sb = 1, i = 0, end = 0;
+    if (live) {
+        uint32_t lo = 0, hi = nb;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid;
+        }
+        b = lo;
+        const uint32_t e0 = __ldg(offsets + b), nbk = __ldg(offsets + b + 1) - e0;
+        sb = (nbk + K - 1) / K;
+        const uint32_t sub = t - __ldg(task_off + b), base = nbk / sb, rem = nbk - base * sb;
+        i = e0 + sub * base + min(sub, rem);
+        end = i + base + (sub < rem ? 1u : 0u);
+    }
+    const uint32_t steps = __reduce_max_sync(0xffffffffu, end - i);
+    uint32_t sign[2] = {0, 0};
+    auto issue = [&](uint32_t step) {
+        const unsigned s = step & 1;
+        const uint32_t bar = smem_u32(&bars[s][warp]);
+        if (i + step < end) {
+            const uint32_t e = __ldg(entries + i + step), idx = e & 0x7fffffffu;
+            sign[s] = e >> 31;
+            mbar_arrive_expect_tx(bar, (uint32_t)sizeof(affine_t));
+            bulk_copy_g2s(smem_u32(&slots[s][tid]), idx < main_count ? points + idx : extra + (idx - main_count), (uint32_t)sizeof(affine_t), bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    };
+    xyzz_t acc = xyzz_identity();
+    if (steps) issue(0);
+    for (uint32_t step = 0; step < steps; step++) {
+        if (step + 1 < steps) issue(step + 1);
+        mbar_wait(smem_u32(&bars[step & 1][warp]), (step >> 1) & 1);
+        if (i + step < end) {
+            const uint4* q4 = reinterpret_cast<const uint4*>(&slots[step & 1][tid]);
+            affine_t q;
+            uint4 v0 = q4[0], v1 = q4[1], v2 = q4[2], v3 = q4[3];
+            q.x.v[0] = v0.x; q.x.v[1] = v0.y; q.x.v[2] = v0.z; q.x.v[3] = v0.w; q.x.v[4] = v1.x; q.x.v[5] = v1.y; q.x.v[6] = v1.z; q.x.v[7] = v1.w;
+            q.y.v[0] = v2.x; q.y.v[1] = v2.y; q.y.v[2] = v2.z; q.y.v[3] = v2.w; q.y.v[4] = v3.x; q.y.v[5] = v3.y; q.y.v[6] = v3.z; q.y.v[7] = v3.w;
+            if (sign[step & 1]) q.y = fe_neg<F>(q.y);
+            acc = xyzz_madd<F>(acc, q);
+        }
+    }
+    if (live) store_xyzz(sb == 1 ? buckets + b : partials + t, acc);
+}
+
 // Balanced first level of the per-bucket sums.  The task partials lie in bucket order; thread u sums the RUN of `run`
 // consecutive partials [u*run, (u+1)*run) segment by segment (a segment = the part of one bucket inside the run) and writes each
 // segment sum back at the segment's first index.  Every thread executes at most run-1 additions whatever the bucket sizes, so a
@@ -629,8 +710,12 @@ int msm_run(const MsmBases& b, const size_t* offs, size_t n_main, const fe* cons
                                                             n_main, n_extra, (uint32_t)main_count, ws.d_offsets, ws.d_counts, ws.d_entries);
     STAGE_MARK(3);
     // 4. accumulation: one task per <= K sorted entries of one bucket
-    k_accumulate<F><<<(unsigned)((NTmax + 127) / 128), 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, ws.d_meta,
-                                                                   d_extra, (uint32_t)main_count, ws.d_buckets, ws.d_partials);
+    if (ws.tma_gather)
+        k_accumulate_tma<F><<<(unsigned)((NTmax + 127) / 128), 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K,
+                                                                           ws.d_meta, d_extra, (uint32_t)main_count, ws.d_buckets, ws.d_partials);
+    else
+        k_accumulate<F><<<(unsigned)((NTmax + 127) / 128), 128, 0, st>>>(b.d_points, ws.d_entries, ws.d_offsets, ws.d_task_off, (uint32_t)NB, K, ws.d_meta,
+                                                                       d_extra, (uint32_t)main_count, ws.d_buckets, ws.d_partials);
     STAGE_MARK(4);
     // 5. per-bucket sums of the task partials (+ giants)
     // giants first: k_giant_finish reads the untouched partial lists, k_run_sum then rewrites partials in place

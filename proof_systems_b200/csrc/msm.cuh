@@ -73,6 +73,7 @@ struct MsmWorkspace {
     uint32_t* d_giant_tickets = nullptr;  // [MSM_MAX_GIANTS] arrival counters (self-resetting)
     uint32_t chunk = 0;               // K override (0: chosen per call so that the tasks fill the machine once)
     uint32_t wave_threads = 0;        // accumulation threads per SM the task count is sized for (0: built-in default)
+    bool tma_gather = false;          // A/B switch: gather the points with the bulk asynchronous copy engine (k_accumulate_tma)
     int sm_count = 148;               // SMs of the device (set by the context)
     bool profile = false;             // record an event after every stage
     cudaEvent_t ev[8] = {};           // MSM_ST_COUNT + 1 stage boundaries

@@ -28,9 +28,8 @@ def test_lagrange_bases_match_reference_files(ctx, orc, request, name):
     evals = orc.to_mont(g.scalar, orc.random_scalars(g.scalar, 2048, seed=31))
     coeffs = zk.Radix2EvaluationDomain(ctx, g.scalar, 2048).ifft(evals)
     assert np.array_equal(srs.commit_evaluations_non_hiding(2048, evals).chunks, srs.commit_non_hiding(coeffs, 1).chunks)
-    # domains larger than the SRS need chunked bases: not on the device path
-    with pytest.raises(zk.ZkError):
-        srs.get_lagrange_basis_from_domain_size(4096)
+    # domains larger than the SRS get chunked bases (ipa.rs:1145-1171): two chunks of 4096 points here
+    assert srs.lagrange_basis_chunks(4096) == 2 and srs.get_lagrange_basis_from_domain_size(4096).shape == (2, 4096, 8)
     srs.close()
 
 
