@@ -132,6 +132,24 @@ def test_sparse_and_short_scalars(ctx, orc, vesta_srs, sparsity, bitlen):
         bases.free()
 
 
+@pytest.mark.parametrize("wb", [-1, 0, 9])
+def test_tma_staged_gather_gives_the_same_points(ctx, orc, vesta_srs, wb):
+    """the measured A/B of profiles/r02_tma_ab.md: accumulation with the gather on the bulk copy engine (option msm_tma) returns
+    what the default kernel and the oracle return — tables, plain bases, and the degenerate one-bucket column"""
+    srs = vesta_srs
+    n = 3000
+    sc = orc.random_scalars(srs.scalar, n, seed=77)
+    ones = np.zeros((n, 4), dtype=np.uint64); ones[:, 0] = 1
+    bases = ctx.upload_bases(srs.cid, srs.g[:n], window_bits=wb)
+    try:
+        ctx.set_option("msm_tma", 1)
+        for scal in (sc, ones):
+            assert np.array_equal(ctx.msm_affine(bases, scal), orc.msm(srs.cid, srs.g[:n], scal))
+    finally:
+        ctx.set_option("msm_tma", 0)
+        bases.free()
+
+
 def test_config2_2_16_pallas(ctx, orc, pallas_srs):
     """BASELINE config 2: 2^16-point Pallas MSM on the real SRS, w = 16 table and the tuned window; one answer is
     pinned by srs/test_pallas.srs (lagrange_bases[65536][i]), the random-scalar answer by the oracle."""

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turn gpurun_out/{launches.csv, prof_*.ncu-rep} into the small text summaries committed under profiles/.
-usage: python tools/summarize_profiles.py r01a   (tag = round + letter)"""
+usage: python tools/summarize_profiles.py r01a [report.ncu-rep ...]   (tag = round + letter; without reports: every .ncu-rep in gpurun_out/)"""
 import collections
 import csv
 import io
@@ -15,7 +15,9 @@ P = os.path.join(ROOT, "profiles")
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+        "launch__registers_per_thread", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tma_cycles_active.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed_op_tma_ld.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+        "smsp__inst_executed.sum", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
         "sm__inst_executed_pipe_lsu.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -49,8 +51,9 @@ if os.path.exists(os.path.join(G, "launches.csv")):
                 f.write(f"| `{o[0][:70]}` | {o[1]} | {o[2]} | {o[3] / 1e3:.1f} |\n")
     print("wrote", f"{tag}_launches.md")
 
+only = [os.path.basename(a) for a in sys.argv[2:]]
 for rep in sorted(os.listdir(G)):
-    if not rep.endswith(".ncu-rep"):
+    if not rep.endswith(".ncu-rep") or (only and rep not in only):
         continue
     raw = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -58,8 +61,9 @@ for rep in sorted(os.listdir(G)):
         continue
     hdr, units = rows[0], rows[1]
     name = rep.replace(".ncu-rep", "")
+    if name.startswith(tag): name = name[len(tag):].lstrip("_")
     with open(os.path.join(P, f"{tag}_{name}.md"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on ({tag}, {rep})\n\nCaptured under `python bench.py --steps 2 --warmup 3` on B200; one column per captured launch.\n\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on ({tag}, {rep})\n\nCaptured under `python tools/prof_cmd.py` (bench-sized inputs, L2 flushed between iterations) on B200; one column per captured launch.\n\n")
         f.write("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(rows) - 2)) + " |\n|---|---|" + "---:|" * (len(rows) - 2) + "\n")
         for w in ["Kernel Name", "Grid Size", "Block Size"] + WANT:
             if w in hdr:
