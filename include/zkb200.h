@@ -225,6 +225,11 @@ size_t zk_ipa_len(const zk_ipa* ipa);
 int zk_ipa_round_lr(zk_ipa* ipa, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12], uint64_t out_ip_l[4], uint64_t out_ip_r[4]);
 int zk_ipa_round_fold(zk_ipa* ipa, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]);
 int zk_ipa_read(zk_ipa* ipa, uint64_t* out_a, uint64_t* out_b, size_t capacity, uint64_t out_g_xyz[12]);
+/* zk_points_fold_dev: the reference's per-round base fold g'[i] = g[i] + [u] g[h + i], i < h (G::combine_one_endo,
+ * poly-commitment/src/ipa.rs:1002-1006, combine.rs:292-342) on device-resident affine points: d_g holds 2h points, d_out
+ * receives h (may not alias d_g), u in Montgomery form of the scalar field.  Not used by zk_srs_open / zk_ipa_* (those never
+ * fold the bases); kept as a parity-tested building block and as the measured alternative. */
+int zk_points_fold_dev(zk_ctx* ctx, int curve_id, const void* d_g, size_t h, const uint64_t u_mont[4], void* d_out);
 
 /* ------------------------------------------------------------------ SRS::open as one call (poly-commitment/src/ipa.rs:823-1061)
  * == <OpeningProof<G> as OpenProof<G>>::open(srs, group_map, plnms, elm, polyscale, evalscale, sponge, rng)  (ipa.rs:1193-1218).

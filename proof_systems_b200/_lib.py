@@ -108,6 +108,7 @@ def lib() -> ctypes.CDLL:
     L.zk_dev_upload.argtypes = [vp, vp, vp, sz]
     L.zk_dev_download.argtypes = [vp, vp, vp, sz]
     L.zk_perm_quotient_dev.argtypes = [vp, i, u, vp, vp, vp, vp, vp, vp, vp, vp, u, vp]
+    L.zk_points_fold_dev.argtypes = [vp, i, vp, sz, vp, vp]
     L.zk_index_cache_load.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.POINTER(vp)]
     L.zk_index_cache_free.argtypes = [vp]
     L.zk_index_cache_free.restype = None
@@ -349,6 +350,11 @@ class Context:
         ps = (ctypes.c_void_p * 7)(*[int(p) for p in d_sigma])
         check(lib().zk_perm_quotient_dev(self._h, field, log_m, pw, ctypes.c_void_p(d_z), ps, ctypes.c_void_p(d_zkpm), _ptr(b), _ptr(g), _ptr(a0), _ptr(sh),
                                          next_shift, ctypes.c_void_p(d_out)))
+
+    def points_fold_dev(self, curve: int, d_g: int, h: int, u_mont, d_out: int):
+        """zk_points_fold_dev: out[i] = g[i] + [u] g[h + i] on device-resident affine points (the reference's per-round base fold)"""
+        u = np.ascontiguousarray(u_mont, dtype=np.uint64).reshape(4)
+        check(lib().zk_points_fold_dev(self._h, curve, ctypes.c_void_p(d_g), h, _ptr(u), ctypes.c_void_p(d_out)))
 
     # ------------------------------------------------------------------ diagnostics
     def field_op(self, field: int, op: str, a, b=None) -> np.ndarray:

@@ -196,6 +196,17 @@ int ipa_round_fold(zk_ipa* s, const uint64_t u_mont[4], const uint64_t u_inv_mon
     return ZK_OK;
 }
 
+
+// g'[i] = g[i] + [k] g[h + i], k canonical; see zk_points_fold_dev
+template <class F> __global__ void __launch_bounds__(64) k_fold_bases(const affine_t* __restrict__ g, size_t h, fe k, affine_t* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h) return;
+    const affine_t lo = g[i], hi = g[h + i];
+    xyzz_t acc = affine_is_inf(hi) ? xyzz_identity() : xyzz_scalar_mul<F>(xyzz_from_affine<F>(hi), k);
+    if (!affine_is_inf(lo)) acc = xyzz_madd<F>(acc, lo);
+    out[i] = xyzz_to_affine<F>(acc);
+}
+
 }  // namespace zkb
 
 extern "C" {
@@ -242,6 +253,32 @@ int zk_ipa_round_fold(zk_ipa* s, const uint64_t u_mont[4], const uint64_t u_inv_
     std::lock_guard<std::mutex> lk(s->ctx->mu);
     ZK_CUDA(cudaSetDevice(s->ctx->device));
     return ipa_round_fold(s, u_mont, u_inv_mont);
+}
+
+// The reference's own per-round base fold, g'[i] = g[i] + [u] g[h + i]  (`G::combine_one_endo`, ipa.rs:1002-1006 /
+// combine.rs:292-342), as a device building block: one thread per output point, a double-and-add chain over the bits of u
+// (leading zeros skipped, so a 128-bit endo-form challenge costs half of a full one) and one inversion back to affine.
+// The opening path does NOT use it (never-folded bases, header comment); it is here so that the two designs can be timed
+// against each other on the same machine (tools/fold_vs_never_fold.py) and is parity-tested like everything else.
+int zk_points_fold_dev(zk_ctx* ctx, int curve_id, const void* d_g, size_t h, const uint64_t u_mont[4], void* d_out) {
+    if (!ctx || !u_mont || ((!d_g || !d_out) && h)) { zk_set_error("points_fold: null argument"); return ZK_ERR_INVALID; }
+    if (curve_id != ZK_PALLAS && curve_id != ZK_VESTA) { zk_set_error("points_fold: unknown curve_id %d", curve_id); return ZK_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    if (h == 0) return ZK_OK;
+    host::hfe um, unit = host::zero();
+    memcpy(&um, u_mont, 32);
+    unit.l[0] = 1;
+    // canonical u = u_mont / R: a Montgomery product with the integer 1
+    const host::hfe uc = curve_id == ZK_PALLAS ? host::mul<host::HFq>(um, unit) : host::mul<host::HFp>(um, unit);
+    fe k;
+    memcpy(&k, &uc, 32);
+    const unsigned blocks = (unsigned)((h + 63) / 64);
+    if (curve_id == ZK_PALLAS) k_fold_bases<FpParams><<<blocks, 64, 0, ctx->stream>>>((const affine_t*)d_g, h, k, (affine_t*)d_out);
+    else k_fold_bases<FqParams><<<blocks, 64, 0, ctx->stream>>>((const affine_t*)d_g, h, k, (affine_t*)d_out);
+    ZK_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return ZK_OK;
 }
 
 // Current state: copies min(len, capacity) leading elements of a and b (Montgomery); out_g_xyz (optional) receives the first

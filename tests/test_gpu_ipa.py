@@ -141,3 +141,27 @@ def test_identity_padding_and_argument_checks(ctx, orc, pallas_srs):
     assert zk.lib().zk_ipa_begin(ctx._h, bases._h, zp, zp, 16, ctypes.byref(out)) == -1        # n is not the padded SRS size
     assert zk.lib().zk_ipa_begin(ctx._h, bases._h, zp, zp, 6, ctypes.byref(out)) == -1         # not a power of two
     bases.free()
+
+
+@pytest.mark.parametrize("name", ["pallas_srs", "vesta_srs"])
+def test_direct_base_fold_building_block(ctx, orc, request, name):
+    """zk_points_fold_dev (the reference's own per-round fold g'[i] = g[i] + [u] g[h + i], ipa.rs:1002-1006) against the oracle's
+    scalar multiplication and addition — full-width and 128-bit (endo-form length) challenges, identity padding on either side."""
+    G = request.getfixturevalue(name)
+    h = 37
+    g = G.g[: 2 * h].copy()
+    g[3] = 0                      # identity in the low half
+    g[h + 5] = 0                  # identity in the high half (the reference's zero padding, ipa.rs:848-850)
+    d_g, d_out = ctx.dev_alloc(g.nbytes), ctx.dev_alloc(g.nbytes // 2)
+    try:
+        ctx.dev_upload(d_g, g)
+        for bits in (255, 128, 1):
+            u = orc.limbs_to_ints(orc.random_scalars(G.scalar, 1, seed=bits))[0] % (1 << bits) or 1
+            ctx.points_fold_dev(G.cid, d_g, h, orc.to_mont(G.scalar, orc.ints_to_limbs([u]))[0], d_out)
+            got = ctx.dev_download(d_out, (h, 8))
+            for i in (0, 3, 5, 11, h - 1):
+                hi = orc.scalar_mul(G.cid, g[h + i], u) if g[h + i].any() else np.zeros(8, dtype=np.uint64)
+                want = g[i] if not hi.any() else (hi if not g[i].any() else orc.affine_add(G.cid, g[i], hi))
+                assert np.array_equal(got[i], want), (bits, i)
+    finally:
+        ctx.dev_free(d_g); ctx.dev_free(d_out)
