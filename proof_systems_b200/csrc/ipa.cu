@@ -120,25 +120,33 @@ template <class FS> static int ipa_expand_and_msm(zk_ipa* s, size_t h, uint64_t 
 
 void ipa_release(zk_ipa* s) {
     if (!s) return;
-    cudaFree(s->d_a);
+    if (s->owns_storage) cudaFree(s->d_a);
     delete s;
 }
 
-int ipa_create(zk_ctx* ctx, const zk_bases* bases, size_t n, zk_ipa** out) {
+// one device allocation: a | b | s0 | s1 | sc_L (+2) | sc_R (+2) | partials (+ two inner products)
+size_t ipa_storage_bytes(size_t n) { return (6 * n + 4 + IP_BLOCKS + 2) * sizeof(fe); }
+
+int ipa_create(zk_ctx* ctx, const zk_bases* bases, size_t n, zk_ipa** out, void* storage) {
     if (n < 1 || (n & (n - 1))) { zk_set_error("ipa: n must be a power of two (the reference pads to a power of two, ipa.rs:848-850)"); return ZK_ERR_INVALID; }
     if (bases->b.n > n || (n > 1 && 2 * bases->b.n <= n)) { zk_set_error("ipa: n = %zu is not the SRS size %zu rounded up to a power of two", n, bases->b.n); return ZK_ERR_INVALID; }
     zk_ipa* s = new zk_ipa();
     s->ctx = ctx; s->curve = bases->b.curve; s->n = s->n0 = n; s->bases = bases;
     const fe one = s->curve == ZK_PALLAS ? fe_one<FqParams>() : fe_one<FpParams>();
-    // one device allocation: a | b | s0 | s1 | sc_L (+2) | sc_R (+2) | partials (+ two inner products)
-    cudaError_t e = cudaMalloc(&s->d_a, (6 * n + 4 + IP_BLOCKS + 2) * sizeof(fe));
+    cudaError_t e = cudaSuccess;
+    if (storage) { s->d_a = (fe*)storage; s->owns_storage = false; }
+    else e = cudaMalloc(&s->d_a, ipa_storage_bytes(n));
     if (e == cudaSuccess) {
         s->d_b = s->d_a + n; s->d_s[0] = s->d_a + 2 * n; s->d_s[1] = s->d_a + 3 * n; s->d_sc = s->d_a + 4 * n; s->d_part = s->d_a + 6 * n + 4;
         if (!ctx->h_scratch) e = cudaMallocHost(&ctx->h_scratch, 256);
         s->h_ip = (fe*)ctx->h_scratch;
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_s[0], &one, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);   // s_0 = (1)
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // `one` is a stack temporary
+    if (e == cudaSuccess) {
+        // s_0 = (1): staged through the context's pinned scratch (one slot per curve: the value never changes), nothing waits for the copy
+        char* slot = (char*)ctx->h_scratch + (s->curve == ZK_PALLAS ? 128 : 160);
+        memcpy(slot, &one, sizeof(fe));
+        e = cudaMemcpyAsync(s->d_s[0], slot, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e != cudaSuccess) {
         zk_set_error("ipa: %s", cudaGetErrorString(e));
         ipa_release(s);

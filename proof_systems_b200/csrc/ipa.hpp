@@ -22,13 +22,16 @@ struct zk_ipa {
     affine_t* d_extra = nullptr;   // [max(1, nwin)][2] rows of (h, U); null for the bare rounds of zk_ipa_*
     fe* d_rand = nullptr;          // [2 * rounds] rand_l, rand_r per round (Montgomery)
     unsigned round = 0;
+    bool owns_storage = true;      // false: a..partials live in a buffer of the context (zk_srs_open reuses it call after call)
 };
 
 
 namespace zkb {
 constexpr unsigned IP_THREADS = 256, IP_BLOCKS = 64;
 // the calls below assume the context lock is held and the device is current
-int ipa_create(zk_ctx* ctx, const zk_bases* bases, size_t n, zk_ipa** out);   // a, b uninitialised device vectors of n elements
+// a, b uninitialised device vectors of n elements; storage: null (own allocation) or ipa_storage_bytes(n) bytes of device memory
+int ipa_create(zk_ctx* ctx, const zk_bases* bases, size_t n, zk_ipa** out, void* storage = nullptr);
+size_t ipa_storage_bytes(size_t n);
 void ipa_release(zk_ipa* s);
 int ipa_round_lr(zk_ipa* s, uint64_t out_l_xyz[12], uint64_t out_r_xyz[12], uint64_t out_ip_l[4], uint64_t out_ip_r[4]);
 int ipa_round_fold(zk_ipa* s, const uint64_t u_mont[4], const uint64_t u_inv_mont[4]);

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128) k_accumulate_tma(const affine_t* __restri
 // and those at the multiples of `run` inside it.  (Slots of single-task buckets hold no partial — k_accumulate wrote the bucket
 // itself — and are segments of their own: read and written back, never mixed.)
 template <class F>
-__global__ void __launch_bounds__(128) k_run_sum(const uint32_t* __restrict__ task_off, uint32_t nb, const uint32_t* __restrict__ meta, uint32_t run,
+__global__ void __launch_bounds__(128, 4) k_run_sum(const uint32_t* __restrict__ task_off, uint32_t nb, const uint32_t* __restrict__ meta, uint32_t run,
                                                  uint32_t smax, xyzz_t* partials) {
     const uint32_t nt = meta[1];
     const uint64_t i0w = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * run;
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128) k_run_sum(const uint32_t* __restrict__ ta
 // throughput-bound and the quad-cooperative variant below only adds work.  run == 0: the bucket's partials are summed one by
 // one; run > 0: k_run_sum ran first and the bucket's value is spread over its first slot and the multiples of `run` inside it.
 template <class F>
-__global__ void __launch_bounds__(128) k_bucket_finish_serial(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
+__global__ void __launch_bounds__(128, 4) k_bucket_finish_serial(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off, uint32_t nb,
                                                               uint32_t K, uint32_t smax, const uint32_t* __restrict__ meta, uint32_t run, xyzz_t* buckets,
                                                               const xyzz_t* __restrict__ partials) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,13 +522,16 @@ __global__ void __launch_bounds__(128, 3) k_gridsum(const xyzz_t* __restrict__ b
     const xyzz_t* bk = buckets + (size_t)g * B;
     const unsigned qd = threadIdx.x >> 2, nq = blockDim.x >> 2;
     const bool row = blockIdx.x < nrows;
-    const uint32_t fixed = row ? blockIdx.x : blockIdx.x - nrows, count = row ? W : nrows;
+    // a column holds B / W buckets — rows 0 .. B/W - 1, except column 0: rows 1 .. B/W (bucket 0 does not exist, bucket B closes
+    // it) — so B / W trips cover every column: a power of two, no trip spent on the odd last row
+    const uint32_t fixed = row ? blockIdx.x : blockIdx.x - nrows, count = row ? W : nrows - 1;
+    const uint32_t shift = (!row && fixed == 0) ? 1u : 0u;
     xyzz_t acc = xyzz_identity();
     for (uint32_t e0 = 0; e0 < count; e0 += nq) {
         const uint32_t e = e0 + qd;
         xyzz_t o = xyzz_identity();
         if (e < count) {
-            const uint32_t i = row ? fixed * W + e : e * W + fixed;
+            const uint32_t i = row ? fixed * W + e : (e + shift) * W + fixed;
             if (i >= 1 && i <= B) o = load_xyzz(bk + (i - 1));
         }
         acc = xyzz_add_quad<F>(acc, o);

@@ -7,6 +7,9 @@
 //     sg = <s, g>            delta = <d s, g> + (d b0) U + r_delta h   ==  (g0 + b0 U) d + r_delta h      (ipa.rs:1030-1038)
 // Host: the O(1)-per-round field arithmetic (u^-1, r_prime, z1, z2), the O(c) tails of the MSMs, the window rows of h and U
 // (255 doublings + one batch inversion), and the caller's sponge / group map behind the callbacks.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -118,6 +121,12 @@ static int open_impl(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, con
     using namespace host;
     zk_ctx* ctx = srs->ctx;
     cudaStream_t st = ctx->stream;
+    // ZKB200_TRACE_OPEN=1: wall-clock split of one call on stderr (diagnostic; tools/open_time.py)
+    static const bool trace = getenv("ZKB200_TRACE_OPEN") != nullptr;
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+    double tr_lr = 0, tr_host = 0, tr_fold = 0;
     const int scalar_field = srs->curve == ZK_PALLAS ? ZK_FQ : ZK_FP;
     const size_t srs_len = srs->n, n0 = (size_t)1 << rounds;
     const MsmBases& gb = srs->g->b;
@@ -200,7 +209,9 @@ static int open_impl(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, con
     }
     // ---- the rounds' state: a and b are built in place
     zk_ipa* s = nullptr;
-    rc = ipa_create(ctx, srs->g, n0, &s);
+    rc = ctx_ensure(&ctx->d_ipa, &ctx->cap_ipa, ipa_storage_bytes(n0));
+    if (rc) return rc;
+    rc = ipa_create(ctx, srs->g, n0, &s, ctx->d_ipa);
     if (rc) return rc;
     struct Guard { zk_ipa* s; ~Guard() { cudaStreamSynchronize(s->ctx->stream); ipa_release(s); } } guard{s};
     std::vector<CombineDesc> all_terms(coeff_terms);
@@ -253,12 +264,15 @@ static int open_impl(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, con
     }
     s->d_extra = d_extra;
     s->d_rand = d_small + 2 * n_elm;
+    const double tr_setup = ms_since(t_begin);
     // ---- the folding rounds (ipa.rs:929-1007)
     std::vector<hfe> chals(rounds), chal_invs(rounds);
     for (unsigned r = 0; r < rounds; r++) {
         uint64_t l_jac[12], r_jac[12];
+        const auto t_r0 = clk::now();
         rc = ipa_round_lr(s, l_jac, r_jac, nullptr, nullptr);
         if (rc) return rc;
+        const auto t_r1 = clk::now();
         uint64_t* lr = out_lr_xy + 16 * (size_t)r;
         zk_jacobian_to_affine(srs->curve, l_jac, lr);
         zk_jacobian_to_affine(srs->curve, r_jac, lr + 8);
@@ -267,9 +281,16 @@ static int open_impl(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, con
         memcpy(&chals[r], u, 32);
         if (is_zero(chals[r])) { zk_set_error("open: zero challenge"); return ZK_ERR_INVALID; }
         chal_invs[r] = inv<HS>(chals[r]);
+        const auto t_r2 = clk::now();
         rc = ipa_round_fold(s, chals[r].l, chal_invs[r].l);
         if (rc) return rc;
+        if (trace) {
+            tr_lr += std::chrono::duration<double, std::milli>(t_r1 - t_r0).count();
+            tr_host += std::chrono::duration<double, std::milli>(t_r2 - t_r1).count();
+            tr_fold += ms_since(t_r2);
+        }
     }
+    const auto t_final = clk::now();
     // ---- a0, r_prime, then sg and delta as one MSM pair (ipa.rs:1009-1038)
     hfe a0;
     ZK_CUDA(cudaMemcpyAsync(s->h_ip, s->d_a, sizeof(fe), cudaMemcpyDeviceToHost, st));
@@ -304,6 +325,9 @@ static int open_impl(zk_srs* srs, const zk_open_poly* polys, size_t n_polys, con
     const hfe z1 = add<HS>(mul<HS>(a0, cc), d), z2 = add<HS>(mul<HS>(r_prime, cc), r_delta);
     memcpy(out_z1, &z1, 32);
     memcpy(out_z2, &z2, 32);
+    if (trace)
+        fprintf(stderr, "[zk_srs_open] setup (combine, b, <a,b>, U rows) %.3f ms | %u rounds: L/R MSM pairs %.3f, host (affine, transcript, 1/u) %.3f, fold launches %.3f | "
+                        "final (sg, delta, z) %.3f | total %.3f ms\n", tr_setup, rounds, tr_lr, tr_host, tr_fold, ms_since(t_final), ms_since(t_begin));
     return ZK_OK;
 }
 

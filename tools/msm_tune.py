@@ -32,7 +32,14 @@ for wb in [int(x) for x in os.environ.get("WINDOWS", "14,15,16").split(",")]:
         rows.append({"window": wb, "wave_threads": wave, "batch": 1, "ms_per_msm": round(t, 4), "stages_us": {a: round(1e3 * b, 1) for a, b in st.items() if a != "ntt"}})
         print(rows[-1], flush=True)
     ctx.set_option("msm_wave_threads", 0)
-    for k in (2, 7, 15):
+    for chunk in [int(x) for x in os.environ.get("CHUNKS", "").split(",") if x]:
+        ctx.set_option("msm_chunk", chunk)
+        t = timed(lambda: ctx.msm_dev(bases, d.data_ptr(), n))
+        ctx.set_profile(True); ctx.msm_dev(bases, d.data_ptr(), n); st = ctx.last_stage_ms(); ctx.set_profile(False)
+        rows.append({"window": wb, "chunk": chunk, "batch": 1, "ms_per_msm": round(t, 4), "stages_us": {a: round(1e3 * b, 1) for a, b in st.items() if a != "ntt"}})
+        print(rows[-1], flush=True)
+    ctx.set_option("msm_chunk", 0)
+    for k in [int(x) for x in os.environ.get("BATCHES", "2,7,15").split(",") if x]:
         import ctypes
         from proof_systems_b200._lib import check, _u64p
         out = np.empty((k, 12), dtype=np.uint64)
