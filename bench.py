@@ -177,6 +177,17 @@ def best_threads(fn, max_threads):
     return best_t
 
 
+def bench_config(n_gpus: int, window_bits: int) -> dict:
+    """The workload both arms run, worded once so that the two JSON lines carry the same `config` (arm-specific settings live under
+    `arm`).  `pippenger_window_bits` is BASELINE config 2's w: the GPU arm's table window; the CPU arm's Pippenger picks ark-ec's own."""
+    wl = "2^16-point Pallas MSM on srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)"
+    if n_gpus > 1:
+        wl += (f"; {n_gpus} ranks, every rank holds the same 2^16 bases and its own 2^16 scalars (the sum over ranks of <s_r, g>): weak scaling, "
+               "one all-gather of the ranks' slice sums (GPU arm: ncclAllGather issued by the library; CPU arm: rank 0 computes one rank's share)")
+    return {"workload": wl, "pippenger_window_bits": window_bits,
+            "l2": "GPU arm: 256 MiB buffer overwritten between timed iterations (flush); CPU arm: n/a"}
+
+
 def run_reference(args):
     """The reference's CPU path for this workload, as restated by the oracle (oracle/pasta_oracle.c: ark-style signed-digit
     Pippenger with window-parallel threads; ark-style radix-2 FFT), all host threads."""
@@ -202,8 +213,8 @@ def run_reference(args):
         "impl": "reference", "metric": "pallas_msm_points_per_s", "value": val, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": msm_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (4 x u64 Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": "2^16-point Pallas MSM on srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)",
-                   "cpu_path": "oracle port of ark-ec 0.5 msm_bigint under the reference's 2-way rayon::join split (ipa.rs:652-662); the reference is Rust and there is no cargo in the image"},
+        "config": bench_config(args.gpus, args.window_bits),
+        "arm": {"cpu_path": "oracle port of ark-ec 0.5 msm_bigint under the reference's 2-way rayon::join split (ipa.rs:652-662); the reference is Rust and there is no cargo in the image"},
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample, "host_threads_available": orc.host_threads()},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ntt": {"metric": "fp_ntt_elements_per_s", "value": N_PTS / ntt_s, "unit": "elements/s", "ms": ntt_s * 1e3,
@@ -528,12 +539,9 @@ def main():
         "metric": "pallas_msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8 x u32 Montgomery limbs)", "data": "synthetic",
-        "config": {
-            "workload": "2^16-point Pallas MSM on srs/pallas.srs generators, uniform Fq scalars (BASELINE config 2)"
-                        + ("" if world == 1 else f"; every rank holds the same 2^16 bases and its own 2^16 scalars (the sum over ranks of <s_r, g>): weak scaling, ncclAllGather of {wb} x 128 B slice sums issued by the library"),
-            "pippenger_window_bits": wb, "window_bits": wb, "resident_table_mib": round(len(bases) * 64 * nwin / 2**20, 1),
-            "l2": "256 MiB buffer overwritten between timed iterations (flush)", "result_matches_cpu_oracle": ok, "all_checks_pass": bool(ok_all),
-        },
+        "config": bench_config(world, args.window_bits),
+        "arm": {"window_bits": wb, "resident_table_mib": round(len(bases) * 64 * nwin / 2**20, 1)},
+        "checks": {"result_matches_cpu_oracle": ok, "all_checks_pass": bool(ok_all)},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": N_PTS * 32, "d2h_bytes_per_step": 128 * max(wb, 1),
                 "ms_per_step": msm_e2e_ms / args.steps},
         "gpu_launches": int(launches_total),

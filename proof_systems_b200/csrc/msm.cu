@@ -527,13 +527,22 @@ __global__ void __launch_bounds__(128, 3) k_gridsum(const xyzz_t* __restrict__ b
     const uint32_t fixed = row ? blockIdx.x : blockIdx.x - nrows, count = row ? W : nrows - 1;
     const uint32_t shift = (!row && fixed == 0) ? 1u : 0u;
     xyzz_t acc = xyzz_identity();
-    for (uint32_t e0 = 0; e0 < count; e0 += nq) {
-        const uint32_t e = e0 + qd;
-        xyzz_t o = xyzz_identity();
+    // The next trip's bucket is in flight while the current one is added (the additions are a dependent chain).  Each lane of the
+    // quad fetches ONE coordinate (32 B) ahead — 8 registers instead of 32 — and the quad reassembles the point with shuffles.
+    const unsigned lane = threadIdx.x & 31, base = lane & ~3u, coord = lane & 3;
+    auto fetch = [&](uint32_t e) {
+        fe part = fe_zero();
         if (e < count) {
             const uint32_t i = row ? fixed * W + e : (e + shift) * W + fixed;
-            if (i >= 1 && i <= B) o = load_xyzz(bk + (i - 1));
+            if (i >= 1 && i <= B) part = load_fe(reinterpret_cast<const fe*>(bk + (i - 1)) + coord);
         }
+        return part;
+    };
+    fe nxt = fetch(qd);
+    for (uint32_t e0 = 0; e0 < count; e0 += nq) {
+        xyzz_t o;
+        o.X = shfl_fe(nxt, base); o.Y = shfl_fe(nxt, base + 1); o.ZZ = shfl_fe(nxt, base + 2); o.ZZZ = shfl_fe(nxt, base + 3);
+        if (e0 + nq < count) nxt = fetch(e0 + nq + qd);
         acc = xyzz_add_quad<F>(acc, o);
     }
     acc = block_tree_sum_quad<F>(acc, sm_tree);
@@ -621,7 +630,8 @@ int msm_run(const MsmBases& b, const size_t* offs, size_t n_main, const fe* cons
         //     of 28 entries run the same additions 1.5x slower than tasks of 8), whatever the batch size;
         // (2) small inputs: never fewer tasks than threads the machine holds at once.
         const size_t n_avg = std::max<size_t>(1, Mmax / NB);
-        size_t k_bal = many_buckets ? std::min<size_t>(64, std::max<size_t>(4, n_avg / 8)) : 64;
+        // (measured at 2^16 points, windows 15 / 16, gpurun_out/msm_tune.json: K = 6..8 beats 4 by 1-3 %: fewer partials for the finish pass)
+        size_t k_bal = many_buckets ? std::min<size_t>(64, std::max<size_t>(6, n_avg / 8)) : 64;
         const size_t slack = std::min<size_t>(NB / 2, capacity / 4);     // sum_b ceil(n_b/K) ~ M/K + (non-empty buckets)/2
         const size_t k_cap = std::max<size_t>(4, (Mmax + capacity - slack - 1) / (capacity - slack));
         K = (uint32_t)std::min(k_bal, k_cap);

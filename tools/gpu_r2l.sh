@@ -7,5 +7,5 @@ ZKB200_TRACE_OPEN=1 timeout 300 python tools/open_time.py 2>&1 | tail -14
 timeout 400 python bench.py --steps 10 --warmup 3 --cpu-seconds 1 --no-extra > gpurun_out/bench_l.log 2>gpurun_out/bench_l.err; echo "bench exit $?"; python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/bench_l.log").read().strip().splitlines()[-1])
-print(d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["stage_ms"], d["config"].get("all_checks_pass"))
+print(d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["stage_ms"], d["checks"])
 PY

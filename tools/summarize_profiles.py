@@ -25,8 +25,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 
-if os.path.exists(os.path.join(G, "launches.csv")):
-    lines = [l for l in open(os.path.join(G, "launches.csv")).read().splitlines() if not l.startswith("==")]
+LAUNCHES = os.environ.get("LAUNCHES", "launches.csv")           # launch list inside gpurun_out/
+CMD = os.environ.get("PROF_CMD", "python bench.py --steps 2 --warmup 3")
+if os.path.exists(os.path.join(G, LAUNCHES)) and not os.environ.get("NO_LAUNCHES"):
+    lines = [l for l in open(os.path.join(G, LAUNCHES)).read().splitlines() if not l.startswith("==")]
     agg = collections.OrderedDict()
     order = []
     for row in csv.DictReader(io.StringIO("\n".join(lines))):
@@ -37,8 +39,8 @@ if os.path.exists(os.path.join(G, "launches.csv")):
         order.append((name, row["Grid Size"], row["Block Size"], float(row["Metric Value"].replace(",", ""))))
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` of `python bench.py --steps 2 --warmup 3`\n\n")
-        f.write("Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  Includes one-time setup (k_build_table,\nk_pow_table, k_ntt_setup) and the L2-flush fill kernel of bench.py.\n\n")
+        f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` of `{CMD}`\n\n")
+        f.write("Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  Includes one-time setup (k_build_table,\nk_pow_table, k_ntt_setup) and the L2-flush fill kernel of the command.\n\n")
         f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k[:80]}` | {c} | {t / 1e3:.1f} | {100 * t / tot:.1f}% |\n")
