@@ -285,6 +285,29 @@ int zk_perm_quotient_dev(zk_ctx* ctx, int field_id, unsigned log_m, const void* 
                          const void* const d_sigma[7], const void* d_zkpm, const uint64_t beta[4], const uint64_t gamma[4],
                          const uint64_t alpha0[4], const uint64_t shifts[28], unsigned next_shift, void* d_out);
 
+/* ------------------------------------------------------------------ constraint evaluator (kimchi's expression framework)
+ * zk_expr_eval_dev replaces Expr::evaluations(&env) (kimchi/src/circuits/expr.rs:1938-2190; call sites kimchi/src/prover.rs:794-892:
+ * every gate's combined constraint and the lookup constraints, evaluated over d4 or d8 and added into t4 / t8).  The expression is
+ * passed in the reference's flat form, the RPN program of PolishToken (expr.rs:819-836, Expr::to_polish), and evaluated at every
+ * point of the output domain by one kernel with the semantics of PolishToken::evaluate (expr.rs:856-940):
+ *   ZK_EXPR_CONST k    push constants[k] — Literal, EndoCoefficient, Mds{row,col} and Challenge terms resolved by the caller
+ *   ZK_EXPR_CELL c     push column (c & 0x7fffffff) at the current row, or the next row when bit 31 is set:
+ *                      evals[(len / out_len * i + domain_mult * shift) % len]   (SubEvals indexing, expr.rs:1976-1982);
+ *                      VanishesOnZeroKnowledgeAndPreviousRows and UnnormalizedLagrangeBasis are columns the caller supplies
+ *   ZK_EXPR_DUP, ZK_EXPR_POW n, ZK_EXPR_ADD, ZK_EXPR_MUL, ZK_EXPR_SUB, ZK_EXPR_STORE, ZK_EXPR_LOAD k   as in the reference
+ *   (SkipIf / SkipIfNot are resolved by the caller: the feature flags are known when the program is built)
+ * Columns are device-resident arrays of Montgomery field elements over a domain `domain_mult` times d1 (len = domain_mult * |d1|,
+ * at least as fine as the output domain); out_len = out_domain_mult * |d1|.  accumulate != 0 adds the result into d_out (t4 += / t8 +=,
+ * prover.rs:876-882).  A program that would underflow the stack, leave more than one value, or index outside its tables is refused
+ * with ZK_ERR_INVALID (ExprError::EmptyStack / the reference's assert) before anything runs; limits: stack 24, cache 96, 64 columns. */
+enum { ZK_EXPR_CONST = 0, ZK_EXPR_CELL = 1, ZK_EXPR_DUP = 2, ZK_EXPR_POW = 3, ZK_EXPR_ADD = 4, ZK_EXPR_MUL = 5, ZK_EXPR_SUB = 6,
+       ZK_EXPR_STORE = 7, ZK_EXPR_LOAD = 8 };
+typedef struct zk_expr_token { uint32_t op; uint32_t arg; } zk_expr_token;
+typedef struct zk_expr_column { const void* d_evals; uint64_t len; uint32_t domain_mult; uint32_t reserved; } zk_expr_column;
+int zk_expr_eval_dev(zk_ctx* ctx, int field_id, const zk_expr_token* tokens, size_t n_tokens, const uint64_t* constants_mont,
+                     size_t n_constants, const zk_expr_column* cols, size_t n_cols, uint64_t out_len, unsigned out_domain_mult,
+                     int accumulate, void* d_out);
+
 /* ------------------------------------------------------------------ cached prover index
  * Device-side ingestion of kimchi's mmap-backed proving-key cache, kimchi/src/cached_prover_index.rs:26-56 ("MINAPK01", format 3):
  * the file stores the index's big arrays — coefficients8 (15 columns), permutation_coefficients8 (7), the gate selectors over d4 / d8,

@@ -170,3 +170,54 @@ static void FN(perm_quot)(const FN(t) *w, size_t w_stride, const FN(t) *z, const
         }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * RPN constraint evaluation: PolishToken::evaluate (kimchi/src/circuits/expr.rs:856-940) run at every index i of an evaluation
+ * domain of out_len points, cells read with the SubEvals indexing of Expr::evaluations (expr.rs:1976-1982):
+ *     cell(col, row) at i = col.evals[(len / out_len * i + domain_mult * shift) % len],  shift = 0 (Curr) | 1 (Next)
+ * Opcodes (the oracle's own numbering; Challenge / Constant terms arrive as literals, feature flags resolved by the caller):
+ *     0 literal k | 1 cell (col | next << 31) | 2 dup | 3 pow n | 4 add | 5 mul | 6 sub | 7 store | 8 load k
+ * Returns 0, or -1 on the reference's failure modes (EmptyStack, final stack length != 1, index out of range).
+ * Checker of zk_expr_eval_dev.
+ */
+static int FN(expr_eval)(const uint32_t *ops, const uint32_t *args, size_t n_tok, const FN(t) *literals, size_t n_lit,
+                         const FN(t) *const *col_evals, const uint64_t *col_len, const uint32_t *col_mult, size_t n_cols,
+                         uint64_t out_len, int accumulate, FN(t) *out, int threads) {
+    int bad = 0;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (uint64_t i = 0; i < out_len; i++) {
+        FN(t) stack[64], cache[256];
+        size_t sp = 0, nc = 0;
+        int fail = 0;
+        for (size_t t = 0; t < n_tok && !fail; t++) {
+            const uint32_t a = args[t];
+            switch (ops[t]) {
+            case 0: if (a >= n_lit || sp >= 64) { fail = 1; break; } stack[sp++] = literals[a]; break;
+            case 1: {
+                const uint32_t c = a & 0x7fffffffu;
+                if (c >= n_cols || sp >= 64) { fail = 1; break; }
+                const uint64_t len = col_len[c], scale = len / out_len;
+                stack[sp++] = col_evals[c][(scale * i + (uint64_t)col_mult[c] * (a >> 31)) % len];
+                break;
+            }
+            case 2: if (sp < 1 || sp >= 64) { fail = 1; break; } stack[sp] = stack[sp - 1]; sp++; break;
+            case 3: if (sp < 1) { fail = 1; break; } { FN(t) r; FN(pow_u64)(&r, &stack[sp - 1], a); stack[sp - 1] = r; } break;
+            case 4: if (sp < 2) { fail = 1; break; } FN(add)(&stack[sp - 2], &stack[sp - 2], &stack[sp - 1]); sp--; break;
+            case 5: if (sp < 2) { fail = 1; break; } FN(mul)(&stack[sp - 2], &stack[sp - 2], &stack[sp - 1]); sp--; break;
+            case 6: if (sp < 2) { fail = 1; break; } FN(sub)(&stack[sp - 2], &stack[sp - 2], &stack[sp - 1]); sp--; break;
+            case 7: if (sp < 1 || nc >= 256) { fail = 1; break; } cache[nc++] = stack[sp - 1]; break;
+            case 8: if (a >= nc || sp >= 64) { fail = 1; break; } stack[sp++] = cache[a]; break;
+            default: fail = 1;
+            }
+        }
+        if (fail || sp != 1) {
+#pragma omp atomic write
+            bad = 1;
+            continue;
+        }
+        if (accumulate) FN(add)(&out[i], &out[i], &stack[0]);
+        else out[i] = stack[0];
+    }
+    return bad ? -1 : 0;
+}
+

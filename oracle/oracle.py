@@ -224,6 +224,27 @@ def perm_quot(fid: int, w, z, sigma, zkpm, beta, gamma, alpha0, shifts, next_shi
     return out
 
 
+def expr_eval(fid: int, ops, args, literals, cols, out_len: int, acc: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
+    """PolishToken::evaluate (expr.rs:856-940) at every index of a domain of out_len points.  ops/args: the program (opcodes
+    0 literal, 1 cell, 2 dup, 3 pow, 4 add, 5 mul, 6 sub, 7 store, 8 load); literals [k, 4] Montgomery; cols: list of
+    (evals [len, 4] Montgomery, domain_mult).  acc: accumulate into a copy of this array.  Raises ValueError on the reference's
+    failure modes (empty stack, final stack != 1, index out of range)."""
+    ops = np.ascontiguousarray(ops, dtype=np.uint32)
+    args = np.ascontiguousarray(args, dtype=np.uint32)
+    lit = np.ascontiguousarray(literals, dtype=np.uint64).reshape(-1, 4)
+    arrs = [np.ascontiguousarray(c[0], dtype=np.uint64).reshape(-1, 4) for c in cols]
+    ptrs = (ctypes.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+    lens = np.array([a.shape[0] for a in arrs] or [0], dtype=np.uint64)
+    mult = np.array([c[1] for c in cols] or [0], dtype=np.uint32)
+    out = np.zeros((out_len, 4), dtype=np.uint64) if acc is None else np.ascontiguousarray(acc, dtype=np.uint64).reshape(out_len, 4).copy()
+    rc = lib().orc_expr_eval(fid, ops.ctypes.data_as(ctypes.c_void_p), args.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(ops)), _p(lit) if lit.size else None,
+                             ctypes.c_size_t(lit.shape[0]), ptrs, lens.ctypes.data_as(ctypes.c_void_p), mult.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(arrs)),
+                             ctypes.c_uint64(out_len), int(acc is not None), _p(out), threads)
+    if rc != 0:
+        raise ValueError("malformed RPN program")
+    return out
+
+
 def dft_naive(fid: int, data: np.ndarray, inverse: bool = False) -> np.ndarray:
     a = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
     n = a.shape[0]

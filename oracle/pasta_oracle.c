@@ -155,6 +155,18 @@ EXPORT void orc_perm_quot(int fid, const uint64_t *w, size_t w_stride, const uin
                      (const fq_t *)gamma, (const fq_t *)alpha0, (const fq_t *)shift, next_shift, log_m, (fq_t *)out, threads);
 }
 
+/* RPN constraint evaluation over a whole domain (kimchi/src/circuits/expr.rs:856-940, :1938-1990); see ntt_impl.h */
+EXPORT int orc_expr_eval(int fid, const uint32_t *ops, const uint32_t *args, size_t n_tok, const uint64_t *literals, size_t n_lit,
+                         const uint64_t *const *col_evals, const uint64_t *col_len, const uint32_t *col_mult, size_t n_cols, uint64_t out_len,
+                         int accumulate, uint64_t *out, int threads) {
+    threads = default_threads(threads);
+    if (fid == 0)
+        return fp_expr_eval(ops, args, n_tok, (const fp_t *)literals, n_lit, (const fp_t *const *)col_evals, col_len, col_mult, n_cols, out_len,
+                            accumulate, (fp_t *)out, threads);
+    return fq_expr_eval(ops, args, n_tok, (const fq_t *)literals, n_lit, (const fq_t *const *)col_evals, col_len, col_mult, n_cols, out_len,
+                        accumulate, (fq_t *)out, threads);
+}
+
 /* ---- curve API ---- */
 EXPORT int orc_on_curve(int cid, const uint64_t *xy) {
     if (cid == 0) return pallas_aff_on_curve((const pallas_aff *)xy);

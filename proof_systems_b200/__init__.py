@@ -15,4 +15,4 @@ from ._lib import (  # noqa: F401
     FP, FQ, PALLAS, VESTA, BASE_FIELD, SCALAR_FIELD, ZkError, Context, Bases, lib, library_path,
     jacobian_to_affine, jacobian_sum,
 )
-from .host import SRS, IndexCache, IpaRounds, OpeningProof, PolyComm, Radix2EvaluationDomain, srs_open  # noqa: F401
+from .host import SRS, ExprProgram, IndexCache, IpaRounds, OpeningProof, PolyComm, Radix2EvaluationDomain, srs_open  # noqa: F401

@@ -109,6 +109,7 @@ def lib() -> ctypes.CDLL:
     L.zk_dev_download.argtypes = [vp, vp, vp, sz]
     L.zk_perm_quotient_dev.argtypes = [vp, i, u, vp, vp, vp, vp, vp, vp, vp, vp, u, vp]
     L.zk_points_fold_dev.argtypes = [vp, i, vp, sz, vp, vp]
+    L.zk_expr_eval_dev.argtypes = [vp, i, vp, sz, vp, sz, vp, sz, ctypes.c_uint64, u, i, vp]
     L.zk_index_cache_load.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.POINTER(vp)]
     L.zk_index_cache_free.argtypes = [vp]
     L.zk_index_cache_free.restype = None
@@ -131,6 +132,16 @@ class IndexHeader(ctypes.Structure):
                 ("lookup_selectors_present", ctypes.c_uint32), ("num_sections", ctypes.c_uint32), ("disable_gates_checks", ctypes.c_int),
                 ("has_verifier_index_digest", ctypes.c_int), ("endo", ctypes.c_uint64 * 4), ("shift", (ctypes.c_uint64 * 4) * 7),
                 ("verifier_index_digest", ctypes.c_uint64 * 4), ("identifier", ctypes.c_char * 512)]
+
+
+class ExprToken(ctypes.Structure):
+    """zk_expr_token (include/zkb200.h)"""
+    _fields_ = [("op", ctypes.c_uint32), ("arg", ctypes.c_uint32)]
+
+
+class ExprColumn(ctypes.Structure):
+    """zk_expr_column (include/zkb200.h)"""
+    _fields_ = [("d_evals", ctypes.c_void_p), ("len", ctypes.c_uint64), ("domain_mult", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class OpenPoly(ctypes.Structure):
@@ -350,6 +361,14 @@ class Context:
         ps = (ctypes.c_void_p * 7)(*[int(p) for p in d_sigma])
         check(lib().zk_perm_quotient_dev(self._h, field, log_m, pw, ctypes.c_void_p(d_z), ps, ctypes.c_void_p(d_zkpm), _ptr(b), _ptr(g), _ptr(a0), _ptr(sh),
                                          next_shift, ctypes.c_void_p(d_out)))
+
+    def expr_eval_dev(self, field: int, tokens, constants, cols, out_len: int, out_domain_mult: int, d_out: int, accumulate: bool = False):
+        """zk_expr_eval_dev: tokens = [(op, arg)], constants [k, 4] Montgomery, cols = [(device pointer, len, domain_mult)]"""
+        tk = (ExprToken * max(1, len(tokens)))(*[ExprToken(int(o), int(a)) for o, a in tokens])
+        cn = np.ascontiguousarray(constants, dtype=np.uint64).reshape(-1, 4)
+        cl = (ExprColumn * max(1, len(cols)))(*[ExprColumn(int(p), int(n), int(m), 0) for p, n, m in cols])
+        check(lib().zk_expr_eval_dev(self._h, field, tk, len(tokens), _ptr(cn) if cn.size else None, cn.shape[0], cl, len(cols), out_len, out_domain_mult,
+                                     int(accumulate), ctypes.c_void_p(d_out)))
 
     def points_fold_dev(self, curve: int, d_g: int, h: int, u_mont, d_out: int):
         """zk_points_fold_dev: out[i] = g[i] + [u] g[h + i] on device-resident affine points (the reference's per-round base fold)"""

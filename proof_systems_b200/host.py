@@ -303,6 +303,41 @@ class IpaRounds:
             pass
 
 
+class ExprProgram:
+    """Builder of the RPN programs zk_expr_eval_dev runs — kimchi's `PolishToken` list (kimchi/src/circuits/expr.rs:819-836) with the
+    Challenge / Constant terms already literal.  Methods are the reference's token names; `evaluations` is Expr::evaluations
+    (expr.rs:1938-1990) on the device.  Opcode numbers are include/zkb200.h's ZK_EXPR_*."""
+    CONST, CELL, DUP, POW, ADD, MUL, SUB, STORE, LOAD = range(9)
+
+    def __init__(self):
+        self.tokens: list[tuple[int, int]] = []
+        self.constants: list[np.ndarray] = []
+        self.n_cached = 0
+
+    def literal(self, x_mont):
+        self.constants.append(np.ascontiguousarray(x_mont, dtype=np.uint64).reshape(4))
+        self.tokens.append((self.CONST, len(self.constants) - 1)); return self
+
+    def cell(self, col: int, next_row: bool = False):
+        self.tokens.append((self.CELL, col | (0x80000000 if next_row else 0))); return self
+
+    def dup(self): self.tokens.append((self.DUP, 0)); return self
+    def pow(self, n: int): self.tokens.append((self.POW, n)); return self
+    def add(self): self.tokens.append((self.ADD, 0)); return self
+    def mul(self): self.tokens.append((self.MUL, 0)); return self
+    def sub(self): self.tokens.append((self.SUB, 0)); return self
+
+    def store(self) -> int:
+        """Store: the top of the stack also goes to the next cache slot; returns the slot for load()"""
+        self.tokens.append((self.STORE, 0)); self.n_cached += 1; return self.n_cached - 1
+
+    def load(self, slot: int): self.tokens.append((self.LOAD, slot)); return self
+
+    def evaluations(self, ctx: Context, field: int, cols, out_len: int, out_domain_mult: int, d_out: int, accumulate: bool = False):
+        """cols: [(device pointer, len, domain_mult)] in the order the program's cell() indices refer to"""
+        ctx.expr_eval_dev(field, self.tokens, np.array(self.constants, dtype=np.uint64).reshape(-1, 4), cols, out_len, out_domain_mult, d_out, accumulate)
+
+
 class Radix2EvaluationDomain:
     """ark_poly::Radix2EvaluationDomain::<F>::new(size) on the device.  `field` is ZK_FP or ZK_FQ."""
 
