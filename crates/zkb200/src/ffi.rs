@@ -39,6 +39,32 @@ pub struct zk_open_transcript {
     pub final_challenge: unsafe extern "C" fn(user: *mut c_void, delta_xy: *const u64, out_c: *mut u64) -> c_int,
 }
 
+pub const ZK_EXPR_CONST: u32 = 0;
+pub const ZK_EXPR_CELL: u32 = 1;
+pub const ZK_EXPR_DUP: u32 = 2;
+pub const ZK_EXPR_POW: u32 = 3;
+pub const ZK_EXPR_ADD: u32 = 4;
+pub const ZK_EXPR_MUL: u32 = 5;
+pub const ZK_EXPR_SUB: u32 = 6;
+pub const ZK_EXPR_STORE: u32 = 7;
+pub const ZK_EXPR_LOAD: u32 = 8;
+
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct zk_expr_token {
+    pub op: u32,
+    pub arg: u32,
+}
+
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct zk_expr_column {
+    pub d_evals: *const c_void,
+    pub len: u64,
+    pub domain_mult: u32,
+    pub reserved: u32,
+}
+
 extern "C" {
     pub fn zk_last_error() -> *const c_char;
     pub fn zk_ctx_create(device_id: c_int, out: *mut *mut zk_ctx) -> c_int;
@@ -60,6 +86,14 @@ extern "C" {
                        polyscale: *const u64, evalscale: *const u64, rng_scalars: *const u64, n_rng_scalars: usize,
                        transcript: *const zk_open_transcript, out_lr_xy: *mut u64, lr_capacity_rounds: usize, out_rounds: *mut usize,
                        out_delta_xy: *mut u64, out_z1: *mut u64, out_z2: *mut u64, out_sg_xy: *mut u64) -> c_int;
+
+    pub fn zk_dev_alloc(ctx: *mut zk_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn zk_dev_free(ctx: *mut zk_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn zk_dev_upload(ctx: *mut zk_ctx, d_dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn zk_dev_download(ctx: *mut zk_ctx, dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
+    pub fn zk_expr_eval_dev(ctx: *mut zk_ctx, field_id: c_int, tokens: *const zk_expr_token, n_tokens: usize, constants_mont: *const u64,
+                            n_constants: usize, cols: *const zk_expr_column, n_cols: usize, out_len: u64, out_domain_mult: c_uint,
+                            accumulate: c_int, d_out: *mut c_void) -> c_int;
 
     pub fn zk_ntt_batch(ctx: *mut zk_ctx, field_id: c_int, data: *mut u64, log_n: c_uint, batch: usize, in_len: usize, inverse: c_int,
                         coset: c_int) -> c_int;

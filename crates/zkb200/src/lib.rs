@@ -7,9 +7,13 @@
 //! * [`GpuRadix2Domain`] implements `ark_poly::EvaluationDomain<F>` by delegation to `Radix2EvaluationDomain`, with
 //!   `fft_in_place` / `ifft_in_place` on field elements sent to `zk_ntt_batch`.
 //!
+//! * [`expr::DeviceColumns`] runs `Expr::evaluations` (kimchi/src/circuits/expr.rs:1938-2190) — the gate and lookup constraints of
+//!   the quotient — as RPN programs over device-resident columns (`zk_expr_eval_dev`).
+//!
 //! Everything called is declared in include/zkb200.h and exported by libzkb200.so; there is no CPU fallback inside the library
 //! (`Ctx::new` fails without a CUDA device) — code that must also run without a GPU keeps using `ipa::SRS`.
 pub mod domain;
+pub mod expr;
 pub mod ffi;
 pub mod marshal;
 pub mod open;

@@ -46,7 +46,7 @@ struct ExprArgs {
     int accumulate;
 };
 
-template <class FS> __global__ void __launch_bounds__(128, 4) k_expr_eval(const __grid_constant__ ExprArgs a) {
+template <class FS> __global__ void __launch_bounds__(128, 8) k_expr_eval(const __grid_constant__ ExprArgs a) {
     fe stack[EXPR_MAX_STACK], cache[EXPR_MAX_CACHE];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.out_len; i += stride) {
@@ -155,7 +155,7 @@ extern "C" int zk_expr_eval_dev(zk_ctx* ctx, int field_id, const zk_expr_token* 
     int sms = 0;
     ZK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     const uint64_t want = (out_len + 127) / 128;
-    const unsigned blocks = (unsigned)std::min<uint64_t>(want, (uint64_t)sms * 4);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(want, (uint64_t)sms * 8);
     if (field_id == ZK_FP) k_expr_eval<FpParams><<<blocks, 128, 0, st>>>(a);
     else k_expr_eval<FqParams><<<blocks, 128, 0, st>>>(a);
     ZK_CUDA(cudaGetLastError());
