@@ -308,6 +308,16 @@ int zk_expr_eval_dev(zk_ctx* ctx, int field_id, const zk_expr_token* tokens, siz
                      size_t n_constants, const zk_expr_column* cols, size_t n_cols, uint64_t out_len, unsigned out_domain_mult,
                      int accumulate, void* d_out);
 
+/* ------------------------------------------------------------------ the quotient's polynomial tail (kimchi/src/prover.rs:905-918)
+ * zk_poly_add_dev                   dst[i] += src[i], i < len — `t4.interpolate() + t8.interpolate()`, `f += &public_poly`,
+ *                                   `quotient += &bnd` on device-resident coefficient vectors (the shorter operand is `src`)
+ * zk_poly_divide_by_vanishing_dev   DensePolynomial::divide_by_vanishing_poly(d1): f (len coefficients) = q (x^n - 1) + r, n = 2^log_n;
+ *                                   writes the len - n coefficients of q to d_quot (nothing when len <= n: q = 0, r = f) and reports
+ *                                   whether r == 0 — the prover's "rest of division by vanishing polynomial" check (prover.rs:910-914).
+ *                                   d_quot may not alias d_f.  The quotient's chunks then go to zk_msm_dev as they lie. */
+int zk_poly_add_dev(zk_ctx* ctx, int field_id, void* d_dst, const void* d_src, size_t len);
+int zk_poly_divide_by_vanishing_dev(zk_ctx* ctx, int field_id, const void* d_f, size_t len, unsigned log_n, void* d_quot, int* remainder_is_zero);
+
 /* ------------------------------------------------------------------ cached prover index
  * Device-side ingestion of kimchi's mmap-backed proving-key cache, kimchi/src/cached_prover_index.rs:26-56 ("MINAPK01", format 3):
  * the file stores the index's big arrays — coefficients8 (15 columns), permutation_coefficients8 (7), the gate selectors over d4 / d8,

@@ -221,3 +221,28 @@ static int FN(expr_eval)(const uint32_t *ops, const uint32_t *args, size_t n_tok
     return bad ? -1 : 0;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * DensePolynomial::divide_by_vanishing_poly(domain) for a plain (non-coset) radix-2 domain of n points, as ark-poly 0.5.0 computes it
+ * (crate not vendored, Cargo.lock:171-279; call site kimchi/src/prover.rs:909): with fewer than n coefficients the quotient is zero
+ * and the polynomial is the remainder; otherwise
+ *     quotient  = coeffs[n..]  and, for every further chunk i = 1 .. len / n - 1, quotient[j] += coeffs[n (i + 1) + j]
+ *     remainder = coeffs[..n]  and remainder[j] += quotient[j]
+ * quot receives len - n coefficients, rem receives n (zero-padded).  Checker of zk_poly_divide_by_vanishing_dev.
+ */
+static void FN(divide_by_vanishing)(const FN(t) *f, size_t len, size_t n, FN(t) *quot, FN(t) *rem) {
+    FN(t) zero;
+    memset(&zero, 0, sizeof zero);
+    if (len < n) {
+        for (size_t j = 0; j < n; j++) rem[j] = j < len ? f[j] : zero;
+        return;
+    }
+    const size_t qlen = len - n;
+    for (size_t j = 0; j < qlen; j++) quot[j] = f[n + j];
+    for (size_t i = 1; i < len / n + (len % n ? 1 : 0); i++)
+        for (size_t j = 0; n * (i + 1) + j < len; j++) FN(add)(&quot[j], &quot[j], &f[n * (i + 1) + j]);
+    for (size_t j = 0; j < n; j++) {
+        rem[j] = f[j];
+        if (j < qlen) FN(add)(&rem[j], &rem[j], &quot[j]);
+    }
+}
+

@@ -245,6 +245,16 @@ def expr_eval(fid: int, ops, args, literals, cols, out_len: int, acc: np.ndarray
     return out
 
 
+def divide_by_vanishing(fid: int, coeffs, log_n: int):
+    """DensePolynomial::divide_by_vanishing_poly(d1) -> (quotient [max(len - n, 0), 4], remainder [n, 4]); coefficients Montgomery"""
+    f = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    n = 1 << log_n
+    quot = np.zeros((max(f.shape[0] - n, 0), 4), dtype=np.uint64)
+    rem = np.zeros((n, 4), dtype=np.uint64)
+    lib().orc_divide_by_vanishing(fid, _p(f), ctypes.c_size_t(f.shape[0]), log_n, _p(quot) if quot.size else None, _p(rem))
+    return quot, rem
+
+
 def dft_naive(fid: int, data: np.ndarray, inverse: bool = False) -> np.ndarray:
     a = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
     n = a.shape[0]

@@ -167,6 +167,12 @@ EXPORT int orc_expr_eval(int fid, const uint32_t *ops, const uint32_t *args, siz
                         accumulate, (fq_t *)out, threads);
 }
 
+/* DensePolynomial::divide_by_vanishing_poly over d1 (kimchi/src/prover.rs:909); see ntt_impl.h */
+EXPORT void orc_divide_by_vanishing(int fid, const uint64_t *f, size_t len, unsigned log_n, uint64_t *quot, uint64_t *rem) {
+    if (fid == 0) fp_divide_by_vanishing((const fp_t *)f, len, (size_t)1 << log_n, (fp_t *)quot, (fp_t *)rem);
+    else fq_divide_by_vanishing((const fq_t *)f, len, (size_t)1 << log_n, (fq_t *)quot, (fq_t *)rem);
+}
+
 /* ---- curve API ---- */
 EXPORT int orc_on_curve(int cid, const uint64_t *xy) {
     if (cid == 0) return pallas_aff_on_curve((const pallas_aff *)xy);

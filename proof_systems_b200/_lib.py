@@ -109,6 +109,8 @@ def lib() -> ctypes.CDLL:
     L.zk_dev_download.argtypes = [vp, vp, vp, sz]
     L.zk_perm_quotient_dev.argtypes = [vp, i, u, vp, vp, vp, vp, vp, vp, vp, vp, u, vp]
     L.zk_points_fold_dev.argtypes = [vp, i, vp, sz, vp, vp]
+    L.zk_poly_add_dev.argtypes = [vp, i, vp, vp, sz]
+    L.zk_poly_divide_by_vanishing_dev.argtypes = [vp, i, vp, sz, u, vp, ctypes.POINTER(ctypes.c_int)]
     L.zk_expr_eval_dev.argtypes = [vp, i, vp, sz, vp, sz, vp, sz, ctypes.c_uint64, u, i, vp]
     L.zk_index_cache_load.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.POINTER(vp)]
     L.zk_index_cache_free.argtypes = [vp]
@@ -369,6 +371,16 @@ class Context:
         cl = (ExprColumn * max(1, len(cols)))(*[ExprColumn(int(p), int(n), int(m), 0) for p, n, m in cols])
         check(lib().zk_expr_eval_dev(self._h, field, tk, len(tokens), _ptr(cn) if cn.size else None, cn.shape[0], cl, len(cols), out_len, out_domain_mult,
                                      int(accumulate), ctypes.c_void_p(d_out)))
+
+    def poly_add_dev(self, field: int, d_dst: int, d_src: int, length: int):
+        """zk_poly_add_dev: dst[i] += src[i] on device-resident coefficient vectors"""
+        check(lib().zk_poly_add_dev(self._h, field, ctypes.c_void_p(d_dst), ctypes.c_void_p(d_src), length))
+
+    def poly_divide_by_vanishing_dev(self, field: int, d_f: int, length: int, log_n: int, d_quot: int) -> bool:
+        """zk_poly_divide_by_vanishing_dev: quotient of f by x^n - 1 into d_quot; returns whether the remainder is zero"""
+        ok = ctypes.c_int()
+        check(lib().zk_poly_divide_by_vanishing_dev(self._h, field, ctypes.c_void_p(d_f), length, log_n, ctypes.c_void_p(d_quot), ctypes.byref(ok)))
+        return bool(ok.value)
 
     def points_fold_dev(self, curve: int, d_g: int, h: int, u_mont, d_out: int):
         """zk_points_fold_dev: out[i] = g[i] + [u] g[h + i] on device-resident affine points (the reference's per-round base fold)"""

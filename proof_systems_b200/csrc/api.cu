@@ -337,6 +337,7 @@ void zk_ctx_destroy(zk_ctx* ctx) {
     if (ctx->d_open) cudaFree(ctx->d_open);
     if (ctx->d_ipa) cudaFree(ctx->d_ipa);
     if (ctx->d_expr) cudaFree(ctx->d_expr);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->d_ntt) cudaFree(ctx->d_ntt);
     if (ctx->d_ntt_tmp) cudaFree(ctx->d_ntt_tmp);
     for (int f = 0; f < 2; f++) for (int d = 0; d < 2; d++) if (ctx->ntt_small[f][d]) cudaFree(ctx->ntt_small[f][d]);

@@ -44,6 +44,7 @@ struct zk_ctx {
     void* h_scratch = nullptr;           // 256 pinned bytes for small read-backs
     void* d_open = nullptr;              // zk_srs_open: staged polynomials | evaluation part | descriptors | extra bases
     size_t cap_open = 0;
+    unsigned* d_flag = nullptr;          // zk_poly_divide_by_vanishing_dev: remainder flag
     void* d_expr = nullptr;              // zk_expr_eval_dev: program | constants | column table
     size_t cap_expr = 0;
     void* d_ipa = nullptr;               // zk_srs_open: the rounds' state (a, b, challenge products, expanded scalars), kept between calls
