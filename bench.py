@@ -48,8 +48,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock + clock-event reasons DURING the timed region.  NVML is polled from a thread every 2 ms (the timed region of a
-    default run is tens of milliseconds: `nvidia-smi -lms` needs about a second before its first line, which is why round 1's
+    """SM clock + clock-event reasons DURING the timed region.  NVML is polled from a thread every 10 ms — often enough for dozens
+    of samples per run, rarely enough that the poll (a driver call plus a GIL hand-over) does not show up in a 0.4 ms step; a 2 ms
+    period produced occasional 3 ms stalls in the end-to-end leg — (the timed region of a default run is tens of milliseconds: `nvidia-smi -lms` needs about a second before its first line, which is why round 1's
     sampler came back empty); nvidia-smi is the fallback when NVML cannot be loaded."""
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
@@ -85,7 +86,7 @@ class ClockSampler:
                 self.samples.append((mhz, tuple(bool(r & m) for m in masks)))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.010)
 
     def start(self):
         self.samples, self.stop_flag = [], False
@@ -101,7 +102,7 @@ class ClockSampler:
         sm = sorted(s[0] for s in self.samples)
         reasons = [n for i, n in enumerate(self.NAMES) if any(s[1][i] for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
-                "source": "NVML, 2 ms period over the timed region"}
+                "source": "NVML, 10 ms period over the timed region"}
 
     def _smi_once(self):
         """fallback: one nvidia-smi query right after the timed region"""
