@@ -205,3 +205,33 @@ impl<'c, Column: Eq + Hash> Drop for DeviceColumns<'c, Column> {
         }
     }
 }
+
+/// The tail of the quotient with t4 / t8 resident (kimchi/src/prover.rs:905-918):
+/// `f = t4.interpolate() + t8.interpolate() + public`, `(quotient, res) = f.divide_by_vanishing_poly(d1)`, `quotient += bnd`.
+/// `public` and `bnd` are resident coefficient vectors of n and 7n elements; returns the quotient's 7n coefficients on the device, or
+/// the prover's error when the remainder does not vanish.
+pub fn quotient_tail<F: GpuField>(
+    ctx: &Ctx,
+    t4: &DeviceEvals,
+    t8: &DeviceEvals,
+    public: &DeviceEvals,
+    bnd: &DeviceEvals,
+    log_n: u32,
+) -> Result<DeviceEvals, String> {
+    let n = 1u64 << log_n;
+    check(unsafe { zk_ntt_dev(ctx.0, F::FIELD_ID, t4.ptr, log_n + 2, 1, 0, 1, 0) })?; // t4.interpolate()
+    check(unsafe { zk_ntt_dev(ctx.0, F::FIELD_ID, t8.ptr, log_n + 3, 1, 0, 1, 0) })?; // t8.interpolate()
+    check(unsafe { zk_poly_add_dev(ctx.0, F::FIELD_ID, t8.ptr, t4.ptr, (4 * n) as usize) })?;
+    check(unsafe { zk_poly_add_dev(ctx.0, F::FIELD_ID, t8.ptr, public.ptr, public.len as usize) })?; // f += &public_poly
+    let mut q = core::ptr::null_mut();
+    check(unsafe { zk_dev_alloc(ctx.0, (7 * n * 32) as usize, &mut q) })?;
+    let mut zero_rem = 0;
+    check(unsafe { zk_poly_divide_by_vanishing_dev(ctx.0, F::FIELD_ID, t8.ptr, (8 * n) as usize, log_n, q, &mut zero_rem) })?;
+    if zero_rem == 0 {
+        unsafe { zk_dev_free(ctx.0, q) };
+        return Err(String::from("rest of division by vanishing polynomial")); // ProverError::Prover, prover.rs:910-914
+    }
+    check(unsafe { zk_poly_add_dev(ctx.0, F::FIELD_ID, q, bnd.ptr, bnd.len as usize) })?; // quotient += &bnd
+    Ok(DeviceEvals { ptr: q, len: 7 * n, domain_mult: 0 })
+}
+

@@ -95,6 +95,14 @@ extern "C" {
                             n_constants: usize, cols: *const zk_expr_column, n_cols: usize, out_len: u64, out_domain_mult: c_uint,
                             accumulate: c_int, d_out: *mut c_void) -> c_int;
 
+    pub fn zk_ntt_dev(ctx: *mut zk_ctx, field_id: c_int, d_data: *mut c_void, log_n: c_uint, batch: usize, in_len: usize, inverse: c_int,
+                      coset: c_int) -> c_int;
+    pub fn zk_ntt_dev_oop(ctx: *mut zk_ctx, field_id: c_int, d_in: *const c_void, in_stride: usize, in_len: usize, d_out: *mut c_void,
+                          log_n: c_uint, batch: usize, inverse: c_int, coset: c_int) -> c_int;
+    pub fn zk_poly_add_dev(ctx: *mut zk_ctx, field_id: c_int, d_dst: *mut c_void, d_src: *const c_void, len: usize) -> c_int;
+    pub fn zk_poly_divide_by_vanishing_dev(ctx: *mut zk_ctx, field_id: c_int, d_f: *const c_void, len: usize, log_n: c_uint,
+                                           d_quot: *mut c_void, remainder_is_zero: *mut c_int) -> c_int;
+
     pub fn zk_ntt_batch(ctx: *mut zk_ctx, field_id: c_int, data: *mut u64, log_n: c_uint, batch: usize, in_len: usize, inverse: c_int,
                         coset: c_int) -> c_int;
 }

@@ -5,6 +5,7 @@
 //   zkb200::PolyComm, BlindedCommitment                                      poly-commitment/src/commitment.rs:47-50,110-116
 //   zkb200::BlindersDontMatch        CommitmentError::BlindersDontMatch      poly-commitment/src/error.rs:3-9
 //   zkb200::Radix2EvaluationDomain   ark_poly::Radix2EvaluationDomain<F>     kimchi/src/prover.rs:41, circuits/domains.rs:24-33
+//   zkb200::Srs::open -> OpeningProof  OpenProof::open / SRS::open          poly-commitment/src/lib.rs:254-298, ipa.rs:823-1061, 1175-1191
 //   zkb200::IpaRounds                the folding loop of SRS::open           poly-commitment/src/ipa.rs:929-1007
 //   zkb200::Bases::msm / msm_bigint  VariableBaseMSM::{msm, msm_bigint}      ipa.rs:649,658,659,672,943,953
 //
@@ -13,8 +14,10 @@
 // elements are 4 x u64 Montgomery limbs, points x||y (identity = zeros): the reference's in-memory form (zkb200.h).
 // There is no CPU fallback: Context's constructor throws Error{ZK_ERR_NO_DEVICE} without a CUDA device.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -99,6 +102,26 @@ struct BlindedCommitment {
     std::vector<Fe> blinders;
 };
 
+// ipa::OpeningProof<G> (ipa.rs:1175-1191)
+struct OpeningProof {
+    std::vector<std::pair<Affine, Affine>> lr;
+    Affine delta{}, sg{};
+    Fe z1{}, z2{};
+};
+// one entry of `plnms`: DensePolynomialOrEvaluations + the blinders of its commitment (utils.rs:18-23); data may live in host or
+// device memory (zk_open_poly); domain_size = 0 for coefficient form
+struct OpenPolynomial {
+    const Fe* data = nullptr;
+    size_t len = 0, domain_size = 0;
+    std::vector<Fe> blinders;
+};
+// the caller's sponge and group map, seen through the three points where SRS::open consults them (ipa.rs:898-910, 962-970, 1040-1041)
+struct OpenTranscript {
+    std::function<Affine(const Fe& combined_inner_product)> u_base;        // absorb shift_scalar(cip); U = group_map.to_group(challenge_fq)
+    std::function<Fe(unsigned round, const Affine& l, const Affine& r)> round;   // absorb l, r; squeeze_prechallenge().to_field(endo_r)
+    std::function<Fe(const Affine& delta)> final_challenge;                // absorb delta; ScalarChallenge(challenge()).to_field(endo_r)
+};
+
 // ipa::SRS<G>{g, h, lagrange_bases}, g and every Lagrange basis resident on the device.
 class Srs {
   public:
@@ -120,6 +143,39 @@ class Srs {
         std::vector<Affine> out(domain_size);
         check(zk_srs_get_lagrange_basis(h_, domain_size, out.empty() ? nullptr : out[0].data(), domain_size));
         return out;
+    }
+    // fn open(&self, group_map, plnms, elm, polyscale, evalscale, sponge, rng) -> OpeningProof<G>   (ipa.rs:823-1061), one zk_srs_open;
+    // rng_scalars: the 2 * rounds + 2 scalars the reference draws from `rng` (rand_l, rand_r per round, then d, r_delta)
+    OpeningProof open(const std::vector<OpenPolynomial>& plnms, const std::vector<Fe>& elm, const Fe& polyscale, const Fe& evalscale,
+                      const std::vector<Fe>& rng_scalars, OpenTranscript& sponge) {
+        std::vector<zk_open_poly> polys(plnms.size());
+        for (size_t k = 0; k < plnms.size(); k++)
+            polys[k] = zk_open_poly{plnms[k].data ? plnms[k].data->data() : nullptr, plnms[k].len, plnms[k].domain_size,
+                                    plnms[k].blinders.empty() ? nullptr : plnms[k].blinders[0].data(), plnms[k].blinders.size()};
+        zk_open_transcript tr{};
+        tr.user = &sponge;
+        tr.u_base = [](void* u, const uint64_t cip[4], uint64_t out[8]) -> int {
+            try { Fe c; std::copy(cip, cip + 4, c.begin()); Affine p = static_cast<OpenTranscript*>(u)->u_base(c); std::copy(p.begin(), p.end(), out); return 0; } catch (...) { return 1; }
+        };
+        tr.round = [](void* u, unsigned r, const uint64_t l[8], const uint64_t rr[8], uint64_t out[4]) -> int {
+            try { Affine a, b; std::copy(l, l + 8, a.begin()); std::copy(rr, rr + 8, b.begin()); Fe c = static_cast<OpenTranscript*>(u)->round(r, a, b); std::copy(c.begin(), c.end(), out); return 0; } catch (...) { return 1; }
+        };
+        tr.final_challenge = [](void* u, const uint64_t d[8], uint64_t out[4]) -> int {
+            try { Affine a; std::copy(d, d + 8, a.begin()); Fe c = static_cast<OpenTranscript*>(u)->final_challenge(a); std::copy(c.begin(), c.end(), out); return 0; } catch (...) { return 1; }
+        };
+        size_t rounds = 0;
+        while ((size_t(1) << rounds) < g_.size()) rounds++;
+        std::vector<uint64_t> lr(16 * rounds);
+        OpeningProof pr;
+        check(zk_srs_open(h_, polys.empty() ? nullptr : polys.data(), polys.size(), elm.empty() ? nullptr : elm[0].data(), elm.size(), polyscale.data(),
+                          evalscale.data(), rng_scalars.empty() ? nullptr : rng_scalars[0].data(), rng_scalars.size(), &tr, lr.data(), rounds, &rounds,
+                          pr.delta.data(), pr.z1.data(), pr.z2.data(), pr.sg.data()));
+        pr.lr.resize(rounds);
+        for (size_t r = 0; r < rounds; r++) {
+            std::copy(lr.begin() + 16 * r, lr.begin() + 16 * r + 8, pr.lr[r].first.begin());
+            std::copy(lr.begin() + 16 * r + 8, lr.begin() + 16 * r + 16, pr.lr[r].second.begin());
+        }
+        return pr;
     }
     // fn commit_non_hiding(&self, plnm, num_chunks) -> PolyComm<G>
     PolyComm commit_non_hiding(const std::vector<Fe>& coeffs, size_t num_chunks) {

@@ -2,7 +2,8 @@
 // a C++ caller would; inputs and outputs are flat little-endian u64 files exchanged with tests/test_gpu_cpp_layer.py.
 //   in : n, then g (n x 8), h (8), coeffs (n + n/2) x 4, evals n x 4, blinders 2 x 4, u 4, u_inv 4
 //   out: commit chunks 2 x 8, masked 2 x 8, commit_evaluations 8, fft of the first n coefficients n x 4 (and the ifft back, n x 4),
-//        msm_bigint(coeffs[0..n]) as affine 8, round-0 L and R as affine 2 x 8, ip_l 4, ip_r 4, a0 4, b0 4, sg 8 after ALL rounds with u
+//        msm_bigint(coeffs[0..n]) as affine 8, round-0 L and R as affine 2 x 8, ip_l 4, ip_r 4, a0 4, b0 4, sg 8 after ALL rounds with u,
+//        Srs::open of the first n coefficients with a stand-in sponge (U = g[7], every challenge = u): l_0, r_0, delta, sg 4 x 8, z1, z2 2 x 4
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -86,6 +87,26 @@ int main(int argc, char** argv) {
         put(out, fin.a0);
         put(out, fin.b0);
         put(out, fin.sg);
+
+        // OpenProof::open through the C++ layer: the three callbacks are the caller's sponge (here a fixed derivation, the same the
+        // Python side of the test uses through ctypes)
+        OpenTranscript sponge;
+        sponge.u_base = [&](const Fe&) { return g[7]; };
+        sponge.round = [&](unsigned, const Affine&, const Affine&) { return u; };
+        sponge.final_challenge = [&](const Affine&) { return u; };
+        OpenPolynomial pl;
+        pl.data = first.data(); pl.len = n; pl.domain_size = 0; pl.blinders = {blinders[0]};
+        size_t k = 0;
+        while ((size_t(1) << k) < n) k++;
+        std::vector<Fe> draws(evals.begin(), evals.begin() + (long)(2 * k + 2));
+        OpeningProof pr = srs.open({pl}, {u, u_inv}, u, u_inv, draws, sponge);
+        if (pr.lr.size() != k) return 7;
+        put(out, pr.lr[0].first);
+        put(out, pr.lr[0].second);
+        put(out, pr.delta);
+        put(out, pr.sg);
+        put(out, pr.z1);
+        put(out, pr.z2);
 
         FILE* f = std::fopen(argv[2], "wb");
         if (!f) return 6;

@@ -59,6 +59,7 @@ def test_cpp_host_layer_matches_the_oracle(orc, pallas_srs, tmp_path):
     fft, back = take(n, 4), take(n, 4)
     msm, lr, ips = take(1, 8)[0], take(2, 8), take(2, 4)
     a0, b0, sg = take(1, 4)[0], take(1, 4)[0], take(1, 8)[0]
+    open_pts, open_z = take(4, 8), take(2, 4)            # Srs::open: l_0, r_0, delta, sg; z1, z2
     assert pos == out.size
     want0 = orc.msm(G.cid, g, orc.ints_to_limbs(coeffs_i[:n]))
     want1 = orc.msm(G.cid, g[: n // 2], orc.ints_to_limbs(coeffs_i[n:]))
@@ -78,3 +79,18 @@ def test_cpp_host_layer_matches_the_oracle(orc, pallas_srs, tmp_path):
     assert orc.fe_int(G.scalar, a0) == sum(x * y for x, y in zip(a, s_inv)) % m
     assert orc.fe_int(G.scalar, b0) == sum(x * y for x, y in zip(b, s)) % m
     assert np.array_equal(sg, orc.msm(G.cid, g, orc.ints_to_limbs(s)))                      # commitment.rs:565-581
+    # OpenProof::open through the C++ layer == the same call through the ctypes layer (itself pinned to the reference's 700-byte
+    # opening proof in tests/test_gpu_srs.py), same stand-in sponge: U = g[7], every challenge = u
+    import proof_systems_b200 as zk
+    ctx = zk.Context(0)
+    try:
+        srs = zk.SRS(ctx, G.cid, g, h)
+        um, uim = mont([u])[0], mont([pow(u, -1, m)])[0]
+        pr = zk.srs_open(srs, [(mont(coeffs_i[:n]), 0, mont(blind_i[:1]))], np.stack([um, uim]), um, uim, mont(evals_i[:2 * k + 2]),
+                         lambda cip: g[7], lambda i, l, r: um, lambda d: um)
+        assert np.array_equal(open_pts[0], pr.lr[0][0]) and np.array_equal(open_pts[1], pr.lr[0][1])
+        assert np.array_equal(open_pts[2], pr.delta) and np.array_equal(open_pts[3], pr.sg)
+        assert np.array_equal(open_z[0], pr.z1) and np.array_equal(open_z[1], pr.z2)
+        srs.close()
+    finally:
+        ctx.close()
