@@ -389,11 +389,6 @@ int zk_ctx_set_option(zk_ctx* ctx, const char* name, long value) {
         for (zk_ctx* c : ctx->children) c->batch = (int)value;
         return ZK_OK;
     }
-    if (!strcmp(name, "ntt_persistent")) {
-        if (value < 0 || value > 1) { zk_set_error("set_option: ntt_persistent %ld outside [0, 1]", value); return ZK_ERR_INVALID; }
-        ntt_set_persistent(value != 0);       // process-wide A/B switch (profiles/r02_ntt_persistent.md)
-        return ZK_OK;
-    }
     if (!strcmp(name, "msm_tma")) {
         if (value < 0 || value > 1) { zk_set_error("set_option: msm_tma %ld outside [0, 1]", value); return ZK_ERR_INVALID; }
         ctx->ws.tma_gather = value != 0;

@@ -1,7 +1,4 @@
 // ntt.cu — kernels and launch plan of the Pasta-field NTT (see ntt.cuh for semantics and reference call sites).
-#include <algorithm>
-#include <type_traits>
-
 #include "ntt.cuh"
 #include "ntt_butterfly.cuh"
 
@@ -111,15 +108,12 @@ template <class F> __global__ void __launch_bounds__(128, 6) k_ntt_pass(NttPassP
     extern __shared__ uint32_t sm[];
     const unsigned S = 1u << p.log_s, SP = S + (S >> 5) + 1;
     const unsigned tid = threadIdx.x, nthr = blockDim.x;
-    // persistent over tiles: the grid is sized so that every CTA transforms the same number of columns (launch_pass) — 1024 tiles
-    // on 888 CTA slots would otherwise run as one full wave plus a 15 % one
-    for (size_t work = blockIdx.x; work < p.n_work; work += gridDim.x) {
-    const size_t by = work / p.n_tiles, tau = work - by * p.n_tiles;
+    const size_t tau = blockIdx.x;
     const size_t t_hi = tau >> p.split_log, t_lo = tau & (((size_t)1 << p.split_log) - 1);
     const size_t in_off = t_hi * p.in_hi + t_lo * p.in_lo;
-    const fe* in = p.in + by * p.in_bs + in_off;
+    const fe* in = p.in + (size_t)blockIdx.y * p.in_bs + in_off;
     const size_t out_off = t_hi * p.out_hi + t_lo * p.out_lo;
-    fe* out = p.out + by * p.out_bs + out_off;
+    fe* out = p.out + (size_t)blockIdx.y * p.out_bs + out_off;
 
     // load, zero-padded by position, written in bit-reversed row order; four independent loads in flight per thread
     for (unsigned r0 = tid; r0 < S; r0 += 4 * nthr) {
@@ -221,8 +215,6 @@ template <class F> __global__ void __launch_bounds__(128, 6) k_ntt_pass(NttPassP
             store_fe(out + k * p.out_rs, v);
         }
     }
-    __syncthreads();       // the tile buffer is reused by the next column
-    }
 }
 
 // x[j] *= g^(+-j) for j < len (forward coset: before the transform; inverse coset: after it)
@@ -242,11 +234,6 @@ __global__ void k_copy_pad(fe* dst, const fe* __restrict__ src, size_t n, size_t
     store_fe(dst + (size_t)blockIdx.y * n + j, j < len ? load_fe_nc(src + (size_t)blockIdx.y * src_bs + j) : fe_zero());
 }
 
-// A/B switch of the balanced persistent grid (zk_ctx_set_option "ntt_persistent"; default on)
-static bool g_ntt_persistent = true;
-void ntt_set_persistent(bool on) { g_ntt_persistent = on; }
-static bool ntt_persistent() { return g_ntt_persistent; }
-
 unsigned ntt_inner_log(unsigned log_n) { return log_n <= 2 * NTT_MAX_LOG_SUB ? 0 : log_n - (log_n + 2) / 3; }
 
 template <class F> static int launch_pass(const NttPassParams& p, size_t tiles, size_t batch_y, cudaStream_t st) {
@@ -256,22 +243,8 @@ template <class F> static int launch_pass(const NttPassParams& p, size_t tiles, 
     if (threads > 128) threads = 128;
     if (threads < 32) threads = 32;
     if (tiles > 0x7fffffffull || batch_y > 65535) { zk_set_error("ntt: %zu x %zu tiles exceed the grid limits", tiles, batch_y); return ZK_ERR_INVALID; }
-    // balanced persistent grid: reps = ceil(work / resident CTA slots) columns per CTA, grid = ceil(work / reps)
-    static int slots_cache[2][12] = {};        // [F][log_s]: resident CTAs of this configuration on the current device
-    int& slots = slots_cache[std::is_same<F, FpParams>::value ? 0 : 1][p.log_s < 12 ? p.log_s : 11];
-    if (slots == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        ZK_CUDA(cudaGetDevice(&dev));
-        ZK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ntt_pass<F>, (int)threads, smem));
-        slots = std::max(1, sms * per_sm);
-    }
-    NttPassParams q = p;
-    q.n_tiles = tiles;
-    q.n_work = tiles * batch_y;
-    const size_t reps = ntt_persistent() ? (q.n_work + (size_t)slots - 1) / (size_t)slots : 1;
-    const size_t grid = (q.n_work + reps - 1) / reps;
-    k_ntt_pass<F><<<(unsigned)grid, threads, smem, st>>>(q);
+    dim3 grid((unsigned)tiles, (unsigned)batch_y);
+    k_ntt_pass<F><<<grid, threads, smem, st>>>(p);
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;
 }

@@ -56,8 +56,6 @@ struct NttPassParams {
     size_t in_len;         // input positions >= in_len read as zero
     int pos_is_row;        // 1: the position is the row index (every tile is a polynomial of its own), 0: the offset inside the polynomial
     int tw_by_lo;
-    size_t n_tiles;        // tiles per polynomial; a CTA walks the linear (polynomial, tile) index with stride gridDim.x
-    size_t n_work;         // n_tiles * batch
 };
 
 template <class F> int ntt_build_small_table(fe* d_small, bool inverse, cudaStream_t st);
@@ -65,7 +63,6 @@ template <class F> int ntt_build_tables(NttTables& t, unsigned log_n, bool inver
 void ntt_free_tables(NttTables& t);
 // log2(n2 * n3) of the three-pass plan for a transform of 2^log_n elements (0: one or two passes, no inner tables needed)
 unsigned ntt_inner_log(unsigned log_n);
-void ntt_set_persistent(bool on);   // A/B: balanced persistent grid (default) against one CTA per tile
 
 // Transform of `batch` polynomials of 2^log_n elements: polynomial b is read from d_in + b * in_bs (its first in_len elements;
 // the rest is taken as zero) and written to d_out + b * 2^log_n.  d_in == d_out (in_bs == 2^log_n) transforms in place.
