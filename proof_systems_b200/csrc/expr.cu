@@ -50,40 +50,50 @@ template <class FS> __global__ void __launch_bounds__(128, 8) k_expr_eval(const 
     fe stack[EXPR_MAX_STACK], cache[EXPR_MAX_CACHE];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.out_len; i += stride) {
-        unsigned sp = 0, nc = 0;
+        // the top of the stack lives in registers (`top`, valid while depth > 0); stack[0 .. depth - 2] holds what is below it: a
+        // binary operator costs one local load instead of two loads and a store
+        unsigned depth = 0, nc = 0;
+        fe top = fe_zero();
 #pragma unroll 1
         for (uint32_t t = 0; t < a.n_tokens; t++) {
             const zk_expr_token tok = a.tokens[t];          // uniform across the grid: one broadcast load
             switch (tok.op) {
-            case ZK_EXPR_CONST: stack[sp++] = load_fe_nc(a.constants + tok.arg); break;
+            case ZK_EXPR_CONST:
+                if (depth) stack[depth - 1] = top;
+                top = load_fe_nc(a.constants + tok.arg); depth++;
+                break;
             case ZK_EXPR_CELL: {
                 const ExprCol c = a.cols[tok.arg & 0x7fffffffu];
                 const uint64_t j = ((uint64_t)c.scale * i + ((tok.arg >> 31) ? c.mult : 0u)) & (c.len - 1);
-                stack[sp++] = load_fe_nc(c.evals + j);
+                if (depth) stack[depth - 1] = top;
+                top = load_fe_nc(c.evals + j); depth++;
                 break;
             }
-            case ZK_EXPR_DUP: stack[sp] = stack[sp - 1]; sp++; break;
+            case ZK_EXPR_DUP: stack[depth - 1] = top; depth++; break;
             case ZK_EXPR_POW: {
-                // x^n, n >= 1: square-and-multiply from the top bit (n = 0 pushes one, like ark's pow)
-                const fe x = stack[sp - 1];
+                // x^n: square-and-multiply from the top bit (n = 0 gives one, like ark's pow)
+                const fe x = top;
                 fe acc = fe_one<FS>();
                 bool started = false;
                 for (int b = 31 - __clz((int)(tok.arg | 1u)); b >= 0; b--) {
                     if (started) acc = fe_mul_call<FS>(acc, acc);
                     if ((tok.arg >> b) & 1u) { acc = started ? fe_mul_call<FS>(acc, x) : x; started = true; }
                 }
-                stack[sp - 1] = acc;
+                top = acc;
                 break;
             }
-            case ZK_EXPR_ADD: sp--; stack[sp - 1] = fe_add<FS>(stack[sp - 1], stack[sp]); break;
-            case ZK_EXPR_SUB: sp--; stack[sp - 1] = fe_sub<FS>(stack[sp - 1], stack[sp]); break;
-            case ZK_EXPR_MUL: sp--; stack[sp - 1] = fe_mul_call<FS>(stack[sp - 1], stack[sp]); break;
-            case ZK_EXPR_STORE: cache[nc++] = stack[sp - 1]; break;
-            case ZK_EXPR_LOAD: stack[sp++] = cache[tok.arg]; break;
+            case ZK_EXPR_ADD: depth--; top = fe_add<FS>(stack[depth - 1], top); break;
+            case ZK_EXPR_SUB: depth--; top = fe_sub<FS>(stack[depth - 1], top); break;
+            case ZK_EXPR_MUL: depth--; top = fe_mul_call<FS>(stack[depth - 1], top); break;
+            case ZK_EXPR_STORE: cache[nc++] = top; break;
+            case ZK_EXPR_LOAD:
+                if (depth) stack[depth - 1] = top;
+                top = cache[tok.arg]; depth++;
+                break;
             default: break;
             }
         }
-        fe r = stack[0];
+        fe r = top;
         if (a.accumulate) r = fe_add<FS>(r, load_fe(a.out + i));
         store_fe(a.out + i, r);
     }

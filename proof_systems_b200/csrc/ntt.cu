@@ -158,6 +158,7 @@ template <class F> __global__ void __launch_bounds__(128, 6) k_ntt_pass(NttPassP
             }
             b = shfl_fe(b, (int)(lane ^ 31u));                    // block B back to natural order
             ntt_lane_last<F>(lane, a, b, p.small);
+            __syncwarp();      // lane t read row 32 + (t ^ 31), which lane t ^ 31 writes below: order the warp's reads before its writes
             uint32_t* qa = sm + ntt_pad((q << 6) + lane);
             uint32_t* qb = sm + ntt_pad((q << 6) + 32 + lane);
 #pragma unroll
