@@ -165,14 +165,19 @@ def cpu_msm(orc, g, scalars, threads):
 
 
 def best_threads(fn, max_threads):
-    """The GPU boxes expose 64-128 hardware threads that are not always all usable (shared host, cgroup quota): run the CPU
-    arm once per candidate thread count and keep the fastest — the baseline gets its best configuration."""
+    """The GPU boxes expose 64-128 hardware threads that are not always all usable (shared host, cgroup quota): after one untimed
+    warm-up (OpenMP pool start-up, page faults), run the CPU arm twice per candidate thread count and keep the count with the best
+    of its two runs — the baseline gets its best configuration, picked from warmed measurements."""
     best, best_t = None, None
     cand = sorted({t for t in (8, 16, 32, 64, 128, max_threads) if t <= max_threads} or {max_threads})
+    fn(cand[-1])
     for t in cand:
-        t0 = time.perf_counter()
-        fn(t)
-        el = time.perf_counter() - t0
+        el = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            fn(t)
+            d = time.perf_counter() - t0
+            el = d if el is None else min(el, d)
         if best is None or el < best:
             best, best_t = el, t
     return best_t

@@ -11,3 +11,11 @@ import json
 d = json.loads(open("gpurun_out/bench_s.log").read().strip().splitlines()[-1])
 print(d["ms_per_step"], d["e2e"]["ms_per_step"], d["ntt"]["ms_per_step"], d["checks"])
 PY
+timeout 900 python tools/replay_kimchi.py > gpurun_out/replay.log 2>&1; echo "replay exit $?"; python - <<'PY'
+import json
+try:
+    d = json.load(open("gpurun_out/replay_kimchi.json"))
+    print("replay total ms", d["total_s"] * 1e3, {k: round(v * 1e3, 3) for k, v in d["stages_s"].items()})
+    print("resident", {k: round(v * 1e3, 3) for k, v in d["resident_stages_s"].items()})
+except Exception as e: print("replay parse failed", e)
+PY

@@ -127,6 +127,37 @@ def replay(zk, orc, ctx, log_n=LOG_N, check=True, n_open_polys=45):
     once()
     total = time.perf_counter() - t0
     report = {"log_n": log_n, "setup_s": setup_s, "total_s": total, "stages_s": dict(out), "kernel_launches": ctx.launch_count}
+
+    # ---- the same NTT stages with the columns RESIDENT: one upload of the 16 evaluation columns, then
+    #      iFFT(n) -> FFT(8n) (out of place into the d8 buffers the quotient reads) -> iFFT(4n) + iFFT(8n), nothing leaves the device.
+    #      Results are compared with what the host-path stages above produced (themselves checked against the oracle below).
+    cols16 = np.concatenate([wit_m, dense[0:1]])
+    d_cols, d_ev8 = ctx.dev_alloc(cols16.nbytes), ctx.dev_alloc(16 * 8 * N * 32)
+    d_big, d_big4 = ctx.dev_alloc(8 * N * 32), ctx.dev_alloc(4 * N * 32)
+    res_r = {}
+
+    def rstage(name, fn):
+        sync = lambda: ctx.dev_download(d_cols, (1, 4))       # a 32-byte read-back: waits for everything queued on the context's stream
+        sync()
+        t0 = time.perf_counter()
+        fn()
+        sync()
+        res_r[name] = time.perf_counter() - t0
+    try:
+        for rep in range(2):                                  # the second pass is the measurement (tables and buffers warm)
+            rstage("upload of the 16 evaluation columns (32 B x 16 n)", lambda: ctx.dev_upload(d_cols, cols16))
+            ctx.dev_upload(d_big, big); ctx.dev_upload(d_big4, big[: 4 * N])
+            rstage("16 iFFT(n), resident", lambda: ctx.ntt_dev(FS, d_cols, log_n, batch=16, inverse=True))
+            rstage("16 FFT(8n), resident", lambda: ctx.ntt_dev_oop(FS, d_cols, N, N, d_ev8, log_n + 3, batch=16))
+            rstage("iFFT(4n) + iFFT(8n), resident", lambda: (ctx.ntt_dev(FS, d_big4, log_n + 2, inverse=True), ctx.ntt_dev(FS, d_big, log_n + 3, inverse=True)))
+        got = ctx.dev_download(d_cols, (16, N, 4))
+        assert np.array_equal(got[:15], p_wit2) and np.array_equal(got[15], p_dense[0]), "resident iFFT(n) differs from the host path"
+        assert np.array_equal(ctx.dev_download(d_ev8, (16, 8 * N, 4)), p_pad), "resident FFT(8n) differs from the host path"
+        assert np.array_equal(ctx.dev_download(d_big, (8 * N, 4)), p_big) and np.array_equal(ctx.dev_download(d_big4, (4 * N, 4)), p_big4)
+    finally:
+        for ptr in (d_cols, d_ev8, d_big, d_big4):
+            ctx.dev_free(ptr)
+    report["resident_stages_s"] = res_r
     if not check:
         srs.close()
         return report
