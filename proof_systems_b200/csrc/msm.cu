@@ -332,6 +332,8 @@ __global__ void __launch_bounds__(128) k_accumulate_tma(const affine_t* __restri
         if (i + step < end) {
             const uint32_t e = __ldg(entries + i + step), idx = e & 0x7fffffffu;
             sign[s] = e >> 31;
+            // the slot was read with ordinary loads two steps ago: order those (generic proxy) before the copy engine's write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(bar, (uint32_t)sizeof(affine_t));
             bulk_copy_g2s(smem_u32(&slots[s][tid]), idx < main_count ? points + idx : extra + (idx - main_count), (uint32_t)sizeof(affine_t), bar);
         } else {
