@@ -3,6 +3,8 @@
   generic gate     kimchi/src/circuits/polynomials/generic.rs:83-120     2 constraints, degree-2, evaluated over d4
   poseidon gate    kimchi/src/circuits/polynomials/poseidon.rs:351-436   15 constraints, x^7 S-box cached with Store/Load,
                                                                           MDS constants, next-row cells; evaluated over d8
+  complete add     kimchi/src/circuits/polynomials/complete_add.rs:103-222   7 constraints, three cached sub-expressions (x21, y21,
+                                                                          x1^2), the literal 1, doublings; degree 3, over d4
   combination      kimchi/src/circuits/argument.rs:201-214               selector * sum_k alpha^(e_k) * constraint_k
 
 Column order used by both programs (what the test uploads):  0..14 witness (d8) | 15..29 coefficients8 (d8) | 30 selector.
@@ -104,3 +106,52 @@ def poseidon_closed_form(P, sel, w, coeff, alpha_pows, mds, i, m, next_shift):
             tot += alpha_pows[idx] * (tgt - (coeff[idx][i] + sum(mds[j][c] * sboxed[c] for c in range(SPONGE_WIDTH))))
             idx += 1
     return sel[i] * tot % P
+
+
+
+def complete_add_gate(p, alpha_pows, one):
+    """selector * sum_k alpha^(e_k) * constraint_k for the 7 constraints of complete_add.rs:108-220; `one` is the Montgomery 1 (T::one());
+    cache.cache(e) stores e the first time it is built and loads it afterwards, as Expr::Cache does in to_polish"""
+    x1, y1, x2, y2, x3, y3, inf, same_x, sv, inf_z, x21_inv = range(W, W + 11)
+    slots = {}
+
+    def cached(name, build):
+        if name in slots:
+            p.load(slots[name])
+        else:
+            build()
+            slots[name] = p.store()
+
+    x21 = lambda: cached("x21", lambda: p.cell(x2).cell(x1).sub())
+    y21 = lambda: cached("y21", lambda: p.cell(y2).cell(y1).sub())
+    x1sq = lambda: cached("x1sq", lambda: p.cell(x1).cell(x1).mul())
+    dbl = lambda: p.dup().add()                                     # Expr::Double
+    cons = [
+        lambda: (p.cell(x21_inv), x21(), p.mul(), p.literal(one).cell(same_x).sub(), p.sub()),          # zero_check: z_inv * z - (1 - r)
+        lambda: (p.cell(same_x), x21(), p.mul()),                                                          #             r * z
+        lambda: (p.cell(same_x), p.cell(sv), dbl(), p.cell(y1).mul(), x1sq(), dbl(), p.sub(), x1sq(), p.sub(), p.mul(),   # same_x * dbl_case
+                 p.literal(one).cell(same_x).sub(), x21(), p.cell(sv).mul(), y21(), p.sub(), p.mul(), p.add()),           # + (1 - same_x) * add_case
+        lambda: (p.cell(x1).cell(x2).add().cell(x3).add().cell(sv).cell(sv).mul().sub()),                  # x1 + x2 + x3 - s^2
+        lambda: (p.cell(sv).cell(x1).cell(x3).sub().mul().cell(y1).sub().cell(y3).sub()),                  # s (x1 - x3) - y1 - y3
+        lambda: (y21(), p.cell(same_x).cell(inf).sub(), p.mul()),                                          # y21 (same_x - inf)
+        lambda: (y21(), p.cell(inf_z).mul().cell(inf).sub()),                                              # y21 inf_z - inf
+    ]
+    p.cell(SELECTOR)
+    for k, build in enumerate(cons):
+        p.literal(alpha_pows[k])
+        build()
+        p.mul()
+        if k:
+            p.add()
+    p.mul()
+    return p
+
+
+def complete_add_closed_form(P, sel, w, alpha_pows, i, scale_w, scale_sel=1):
+    j = scale_w * i
+    x1, y1, x2, y2, x3, y3, inf, same_x, s, inf_z, x21_inv = (w[k][j] for k in range(11))
+    x21, y21, x1sq = x2 - x1, y2 - y1, x1 * x1
+    cons = [x21_inv * x21 - (1 - same_x), same_x * x21,
+            same_x * (2 * s * y1 - 2 * x1sq - x1sq) + (1 - same_x) * (x21 * s - y21),
+            x1 + x2 + x3 - s * s, s * (x1 - x3) - y1 - y3, y21 * (same_x - inf), y21 * inf_z - inf]
+    return sel[scale_sel * i] * sum(a * c for a, c in zip(alpha_pows, cons)) % P

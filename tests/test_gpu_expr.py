@@ -1,8 +1,8 @@
 """SURVEY.md §8f row 3, the evaluator: kimchi's expression framework on the device.  zk_expr_eval_dev runs the reference's RPN form
 of a constraint (PolishToken, kimchi/src/circuits/expr.rs:819-836) at every point of d4 / d8 with the semantics of
 PolishToken::evaluate (:856-940) and the cell indexing of Expr::evaluations (:1938-1990).  Checked bit for bit against the oracle's
-own restatement (pinned to the gates' closed forms in tests/test_oracle_expr.py) on the programs of two real gates
-(generic: kimchi/src/circuits/polynomials/generic.rs:83-120; poseidon: poseidon.rs:351-436), on random programs that use every
+own restatement (pinned to the gates' closed forms in tests/test_oracle_expr.py) on the programs of three real gates
+(generic: kimchi/src/circuits/polynomials/generic.rs:83-120; poseidon: poseidon.rs:351-436; complete add: complete_add.rs:103-222), on random programs that use every
 opcode, on the permutation quotient written as a program (against the dedicated kernel), and on the reference's failure modes."""
 import numpy as np
 import pytest
@@ -50,6 +50,21 @@ def test_generic_gate_over_d4(ctx, orc, fid, log_n):
         d_out = r.alloc(4 * n * 32)
         prog = gp.generic_gate(zk.ExprProgram(), alphas)
         prog.evaluations(ctx, fid, cols, 4 * n, 4, d_out)
+        assert np.array_equal(ctx.dev_download(d_out, (4 * n, 4)), want)
+
+
+@pytest.mark.parametrize("fid,log_n", [(1, 6), (0, 11)])
+def test_complete_add_gate_over_d4(ctx, orc, fid, log_n):
+    """complete_add.rs:103-222: three cached sub-expressions reused across constraints, the literal 1, doublings (Dup + Add)"""
+    n, m, rnd, w, co = _columns(orc, fid, log_n, 21)
+    sel4, alphas = rnd(4 * n, 960), rnd(7, 961)
+    one = orc.to_mont(fid, orc.ints_to_limbs([1]))[0]
+    rec = gp.complete_add_gate(gp.Recorder(), alphas, one)
+    want = orc.expr_eval(fid, rec.ops, rec.args, rec.literals, [(a, 8) for a in w + co] + [(sel4, 4)], 4 * n)
+    with Resident(ctx) as r:
+        cols = [(r.put(a), m, 8) for a in w + co] + [(r.put(sel4), 4 * n, 4)]
+        d_out = r.alloc(4 * n * 32)
+        gp.complete_add_gate(zk.ExprProgram(), alphas, one).evaluations(ctx, fid, cols, 4 * n, 4, d_out)
         assert np.array_equal(ctx.dev_download(d_out, (4 * n, 4)), want)
 
 

@@ -49,6 +49,21 @@ def test_poseidon_gate_over_d8_matches_the_closed_form_and_accumulates(orc, fid_
     assert ints(acc) == [2 * x % P for x in got]
 
 
+@pytest.mark.parametrize("fid_name", ["FP", "FQ"])
+def test_complete_add_gate_over_d4_matches_the_closed_form(orc, fid_name):
+    fid = getattr(orc, fid_name)
+    n, m, P, rnd, w, co, ints = _setup(orc, fid, 4, 21)
+    sel4, alphas = rnd(4 * n, 960), rnd(7, 961)
+    one = orc.to_mont(fid, orc.ints_to_limbs([1]))[0]
+    rec = gp.complete_add_gate(gp.Recorder(), alphas, one)
+    assert rec.n_cached == 3
+    cols = [(a, 8) for a in w] + [(a, 8) for a in co] + [(sel4, 4)]
+    got = ints(orc.expr_eval(fid, rec.ops, rec.args, rec.literals, cols, 4 * n))
+    wi, si, ai = [ints(a) for a in w], ints(sel4), ints(alphas)
+    for i in list(range(0, 4 * n, 5)) + [4 * n - 1]:
+        assert got[i] == gp.complete_add_closed_form(P, si, wi, ai, i, 2), i
+
+
 def test_failure_modes_of_the_reference(orc):
     one = orc.to_mont(orc.FP, orc.ints_to_limbs([1]))
     col = [(orc.to_mont(orc.FP, orc.random_scalars(orc.FP, 8, seed=3)), 8)]
