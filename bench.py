@@ -277,12 +277,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """per-step CUDA events on the launching stream, L2 flushed between steps (outside the timed span); total ms"""
+    def timed(fn, steps, collective=False):
+        """per-step CUDA events on the launching stream, L2 flushed between steps (outside the timed span); total ms.
+        collective: the step contains a cross-rank exchange — the ranks are aligned before every step"""
         tot = 0.0
         for _ in range(steps):
             flush_l2()
             torch.cuda.synchronize()
+            if world > 1 and collective:
+                # every rank enters the step together: the untimed flush / host work of the slowest rank must not be billed to the
+                # others' collective (at N = 8 that skew was +0.3 ms per step); the rendezvous itself is outside the event span
+                dist.barrier()
+                torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             fn()
@@ -351,11 +357,11 @@ def main():
         ntt_e2e()
     barrier()
     launches0 = ctx.launch_count
-    msm_ms = timed(step_resident, args.steps)
+    msm_ms = timed(step_resident, args.steps, collective=True)
     barrier()
     ntt_ms = timed(ntt_resident, args.steps)
     barrier()
-    msm_e2e_ms = timed(step_e2e, args.steps)
+    msm_e2e_ms = timed(step_e2e, args.steps, collective=True)
     barrier()
     ntt_e2e_ms = timed(ntt_e2e, args.steps)
     barrier()
@@ -469,9 +475,9 @@ def main():
         for _ in range(3):
             r4 = sh4(b4, d_sc4.data_ptr(), hi - lo)
         barrier()
-        t4_res = max_over_ranks(timed(lambda: sh4(b4, d_sc4.data_ptr(), hi - lo), steps4)) / steps4
+        t4_res = max_over_ranks(timed(lambda: sh4(b4, d_sc4.data_ptr(), hi - lo), steps4, collective=True)) / steps4
         barrier()
-        t4_e2e = max_over_ranks(timed(lambda: sh4(b4, h_sc4.data_ptr(), hi - lo), steps4)) / steps4
+        t4_e2e = max_over_ranks(timed(lambda: sh4(b4, h_sc4.data_ptr(), hi - lo), steps4, collective=True)) / steps4
         barrier()
         a4, st4 = stage_profile(lambda: ctx.msm_dev(b4, d_sc4.data_ptr(), hi - lo), 3)
         ach4 = MSM_BYTES_PER_POINT * (hi - lo) / (a4 * 1e-3) / 1e9
