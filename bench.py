@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -48,14 +47,14 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock + clock-event reasons DURING the timed region.  NVML is polled from a thread every 10 ms — often enough for dozens
-    of samples per run, rarely enough that the poll (a driver call plus a GIL hand-over) does not show up in a 0.4 ms step; a 2 ms
-    period produced occasional 3 ms stalls in the end-to-end leg — (the timed region of a default run is tens of milliseconds: `nvidia-smi -lms` needs about a second before its first line, which is why round 1's
-    sampler came back empty); nvidia-smi is the fallback when NVML cannot be loaded."""
+    """SM clock + clock-event reasons DURING the timed region: one NVML query between every two timed steps, from the main thread,
+    outside the CUDA-event span.  (A polling thread — every 2 ms, then every 10 ms — was measured to stall a step by ~3 ms whenever
+    a query coincided with it: NVML and the CUDA runtime share driver locks, and on an 8-GPU box with 8 ranks one such stall per
+    20-step leg cost 0.17 ms per step on every rank, tools/diag_scale.py.)  nvidia-smi is the fallback when NVML cannot be loaded."""
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.samples, self.stop_flag, self.thread, self.h, self.nv = index, [], False, None, None, None
+        self.index, self.samples, self.h, self.nv = index, [], None, None
         self.sm_max = None
         try:
             import pynvml
@@ -72,37 +71,33 @@ class ClockSampler:
         except Exception:
             self.h = None
 
-    def _poll(self):
+    def sample(self):
+        """one query; called between timed steps (the GPU has just run a step and the L2 flush)"""
+        if self.h is None:
+            return
         nv = self.nv
         masks = (nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
                  nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap)
-        while not self.stop_flag:
+        try:
+            mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((mhz, tuple(bool(r & m) for m in masks)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                pass
-            time.sleep(0.010)
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.samples.append((mhz, tuple(bool(r & m) for m in masks)))
+        except Exception:
+            pass
 
     def start(self):
-        self.samples, self.stop_flag = [], False
-        if self.h is not None:
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
+        self.samples = []
 
     def stop(self):
         if self.h is None:
             return self._smi_once()
-        self.stop_flag = True
-        self.thread.join(timeout=2)
         sm = sorted(s[0] for s in self.samples)
         reasons = [n for i, n in enumerate(self.NAMES) if any(s[1][i] for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
-                "source": "NVML, 10 ms period over the timed region"}
+                "source": "NVML, one query between every two timed steps (outside the event span)"}
 
     def _smi_once(self):
         """fallback: one nvidia-smi query right after the timed region"""
@@ -283,6 +278,8 @@ def main():
         tot = 0.0
         for _ in range(steps):
             flush_l2()
+            if rank == 0:
+                sampler.sample()        # the GPU is busy with the flush right behind the previous step: clocks under load
             torch.cuda.synchronize()
             if world > 1 and collective:
                 # every rank enters the step together: the untimed flush / host work of the slowest rank must not be billed to the
