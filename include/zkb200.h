@@ -16,8 +16,10 @@
  *   curve_id        ZK_PALLAS (coordinates Fp, scalars Fq), ZK_VESTA (coordinates Fq, scalars Fp)
  *
  * Every function returns 0 on success or a negative ZK_ERR_* code; zk_last_error() describes the last failure of
- * the calling thread.  Nothing unwinds across the boundary.  A context serialises its own calls (the 15 concurrent
- * rayon callers of kimchi/src/prover.rs:329-351 may share one context; use several contexts for concurrency).
+ * the calling thread.  Nothing unwinds across the boundary.  A context is a pool of lanes (stream + workspace each; option
+ * "ctx_lanes", default 4): calls that take HOST pointers from different threads — the 15 concurrent rayon callers of
+ * kimchi/src/prover.rs:329-351 — each take a free lane and overlap on the GPU; calls on an external stream, calls that take
+ * device pointers and zk_srs_open (which holds the context across its callbacks) are serialised on the primary lane.
  * There is NO CPU fallback: without a CUDA device zk_ctx_create fails with ZK_ERR_NO_DEVICE.
  */
 #ifndef ZKB200_H
