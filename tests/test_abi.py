@@ -29,6 +29,39 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(L, s), f"{s} declared in include/zkb200.h but not exported by libzkb200.so"
 
 
+def test_rust_shim_binds_only_what_the_header_declares():
+    """crates/zkb200/src/ffi.rs (the reference-side binding, shipped as source: no Rust toolchain in this image) must name only
+    functions the header declares and the library exports, with the header's argument counts; its constants must equal the header's"""
+    ffi = open(os.path.join(ROOT, "crates", "zkb200", "src", "ffi.rs")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "zkb200.h")).read(), flags=re.S)
+    rust = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (zk_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]*)?;", ffi, flags=re.S)}
+    assert len(rust) >= 20
+    declared = declared_symbols()
+    import proof_systems_b200 as zk
+    L = zk.lib()
+    for name, args in rust.items():
+        assert name in declared and hasattr(L, name), name
+        c_args = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", hdr, flags=re.S).group(1)
+        n_c = 0 if c_args.strip() in ("", "void") else c_args.count(",") + 1
+        n_r = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
+        assert n_c == n_r, (name, n_c, n_r)
+    for const, val in re.findall(r"pub const (ZK_[A-Z_]+): (?:c_int|u32) = (-?\d+);", ffi):
+        m = re.search(r"#define\s+" + const + r"\s+\(?(-?\d+)\)?", hdr) or re.search(const + r"\s*=\s*(-?\d+)", hdr)
+        assert m and int(m.group(1)) == int(val), const
+    # every zk_* call in the crate's other files is declared in ffi.rs
+    src_dir = os.path.join(ROOT, "crates", "zkb200", "src")
+    for f in os.listdir(src_dir):
+        if f.endswith(".rs") and f != "ffi.rs":
+            code = re.sub(r"//.*", "", open(os.path.join(src_dir, f)).read())
+            for called in set(re.findall(r"\b(zk_[a-z0-9_]+)\s*\(", code)):
+                assert called in rust, (f, called)
+    # every source file of the crate is listed in lib.rs
+    lib_rs = open(os.path.join(ROOT, "crates", "zkb200", "src", "lib.rs")).read()
+    for f in os.listdir(os.path.join(ROOT, "crates", "zkb200", "src")):
+        if f.endswith(".rs") and f != "lib.rs":
+            assert f"pub mod {f[:-3]};" in lib_rs, f
+
+
 def test_no_cpu_fallback():
     import torch
     import proof_systems_b200 as zk
