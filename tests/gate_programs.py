@@ -5,6 +5,9 @@
                                                                           MDS constants, next-row cells; evaluated over d8
   complete add     kimchi/src/circuits/polynomials/complete_add.rs:103-222   7 constraints, three cached sub-expressions (x21, y21,
                                                                           x1^2), the literal 1, doublings; degree 3, over d4
+  endomul scalar   kimchi/src/circuits/polynomials/endomul_scalar.rs:174-220  11 constraints: Horner polynomials with the rational
+                                                                          literals 11/6, -5/2, 2/3, eight cached c_func values, long
+                                                                          double-and-add folds; degree 4
   combination      kimchi/src/circuits/argument.rs:201-214               selector * sum_k alpha^(e_k) * constraint_k
 
 Column order used by both programs (what the test uploads):  0..14 witness (d8) | 15..29 coefficients8 (d8) | 30 selector.
@@ -155,3 +158,81 @@ def complete_add_closed_form(P, sel, w, alpha_pows, i, scale_w, scale_sel=1):
             same_x * (2 * s * y1 - 2 * x1sq - x1sq) + (1 - same_x) * (x21 * s - y21),
             x1 + x2 + x3 - s * s, s * (x1 - x3) - y1 - y3, y21 * (same_x - inf), y21 * inf_z - inf]
     return sel[scale_sel * i] * sum(a * c for a, c in zip(alpha_pows, cons)) % P
+
+
+
+def endomul_scalar_literals(P):
+    """the field constants of endomul_scalar.rs:188-197 as integers mod P"""
+    inv = lambda a: pow(a, -1, P)
+    c_coeffs = [0, 11 * inv(6) % P, (-5) * inv(2) % P, 2 * inv(3) % P]
+    crumb_over_x = [(-6) % P, 11, (-6) % P, 1]
+    d_minus_c = [(-1) % P, 3, (-1) % P]
+    return c_coeffs, crumb_over_x, d_minus_c
+
+
+def endomul_scalar_gate(p, alpha_pows, lit):
+    """selector * sum_k alpha^(e_k) * constraint_k, the 11 constraints of endomul_scalar.rs:178-219.  `lit(v)` gives the Montgomery
+    limbs of the integer v.  polynomial(coeffs, x) is the reference's Horner fold from T::zero() (endomul_scalar.rs:57-62)."""
+    P = lit.modulus
+    c_coeffs, crumb_over_x, d_minus_c = endomul_scalar_literals(P)
+    n0, n8, a0, b0, a8, b8 = range(W, W + 6)
+    xs = [W + 6 + i for i in range(8)]
+
+    def polynomial(coeffs, x):
+        p.literal(lit(0))                                   # T::zero()
+        for c in reversed(coeffs):
+            p.cell(x).mul().literal(lit(c)).add()           # acc * x + literal(c)
+
+    slots = [None] * 8
+
+    def c_func(i):                                           # cache.cache(polynomial(c_coeffs, xs[i]))
+        if slots[i] is None:
+            polynomial(c_coeffs, xs[i])
+            slots[i] = p.store()
+        else:
+            p.load(slots[i])
+
+    dbl = lambda: p.dup().add()
+
+    def n8_constraint():
+        p.cell(n0)
+        for x in xs:
+            dbl(); dbl(); p.cell(x).add()
+        p.cell(n8).sub()
+
+    def a8_constraint():
+        p.cell(a0)
+        for i in range(8):
+            dbl(); c_func(i); p.add()
+        p.cell(a8).sub()
+
+    def b8_constraint():
+        p.cell(b0)
+        for i in range(8):
+            dbl(); c_func(i); polynomial(d_minus_c, xs[i]); p.add(); p.add()     # acc.double() + (c_func + polynomial(d - c))
+        p.cell(b8).sub()
+
+    cons = [n8_constraint, a8_constraint, b8_constraint] + [(lambda x=x: (polynomial(crumb_over_x, x), p.cell(x).mul())) for x in xs]
+    p.cell(SELECTOR)
+    for k, build in enumerate(cons):
+        p.literal(alpha_pows[k])
+        build()
+        p.mul()
+        if k:
+            p.add()
+    p.mul()
+    return p
+
+
+def endomul_scalar_closed_form(P, sel, w, alpha_pows, i):
+    c_coeffs, crumb_over_x, d_minus_c = endomul_scalar_literals(P)
+    poly = lambda cs, x: sum(c * pow(x, k, P) for k, c in enumerate(cs)) % P
+    n0, n8, a0, b0, a8, b8 = (w[k][i] for k in range(6))
+    xs = [w[6 + k][i] for k in range(8)]
+    n, a, b = n0, a0, b0
+    for x in xs:
+        n = (4 * n + x) % P
+        a = (2 * a + poly(c_coeffs, x)) % P
+        b = (2 * b + poly(c_coeffs, x) + poly(d_minus_c, x)) % P
+    cons = [n - n8, a - a8, b - b8] + [poly(crumb_over_x, x) * x for x in xs]
+    return sel[i] * sum(al * c for al, c in zip(alpha_pows, cons)) % P

@@ -1,8 +1,9 @@
 """SURVEY.md §8f row 3, the evaluator: kimchi's expression framework on the device.  zk_expr_eval_dev runs the reference's RPN form
 of a constraint (PolishToken, kimchi/src/circuits/expr.rs:819-836) at every point of d4 / d8 with the semantics of
 PolishToken::evaluate (:856-940) and the cell indexing of Expr::evaluations (:1938-1990).  Checked bit for bit against the oracle's
-own restatement (pinned to the gates' closed forms in tests/test_oracle_expr.py) on the programs of three real gates
-(generic: kimchi/src/circuits/polynomials/generic.rs:83-120; poseidon: poseidon.rs:351-436; complete add: complete_add.rs:103-222), on random programs that use every
+own restatement (pinned to the gates' closed forms in tests/test_oracle_expr.py) on the programs of four real gates
+(generic: kimchi/src/circuits/polynomials/generic.rs:83-120; poseidon: poseidon.rs:351-436; complete add: complete_add.rs:103-222;
+endomul scalar: endomul_scalar.rs:174-220), on random programs that use every
 opcode, on the permutation quotient written as a program (against the dedicated kernel), and on the reference's failure modes."""
 import numpy as np
 import pytest
@@ -66,6 +67,27 @@ def test_complete_add_gate_over_d4(ctx, orc, fid, log_n):
         d_out = r.alloc(4 * n * 32)
         gp.complete_add_gate(zk.ExprProgram(), alphas, one).evaluations(ctx, fid, cols, 4 * n, 4, d_out)
         assert np.array_equal(ctx.dev_download(d_out, (4 * n, 4)), want)
+
+
+class _Lit:
+    def __init__(self, orc, fid):
+        self.orc, self.fid, self.modulus = orc, fid, (orc.FP_MODULUS if fid == orc.FP else orc.FQ_MODULUS)
+    def __call__(self, v):
+        return self.orc.to_mont(self.fid, self.orc.ints_to_limbs([v % self.modulus]))[0]
+
+
+@pytest.mark.parametrize("fid,log_n", [(0, 7), (1, 10)])
+def test_endomul_scalar_gate_over_d8(ctx, orc, fid, log_n):
+    """endomul_scalar.rs:174-220: 11 constraints with rational literals (11/6, -5/2, 2/3), Horner folds from zero, eight cached values"""
+    n, m, rnd, w, co = _columns(orc, fid, log_n, 33)
+    sel8, alphas = rnd(m, 970), rnd(11, 971)
+    rec = gp.endomul_scalar_gate(gp.Recorder(), alphas, _Lit(orc, fid))
+    want = orc.expr_eval(fid, rec.ops, rec.args, rec.literals, [(a, 8) for a in w + co] + [(sel8, 8)], m)
+    with Resident(ctx) as r:
+        cols = [(r.put(a), m, 8) for a in w + co] + [(r.put(sel8), m, 8)]
+        d_out = r.alloc(m * 32)
+        gp.endomul_scalar_gate(zk.ExprProgram(), alphas, _Lit(orc, fid)).evaluations(ctx, fid, cols, m, 8, d_out)
+        assert np.array_equal(ctx.dev_download(d_out, (m, 4)), want)
 
 
 @pytest.mark.parametrize("fid,log_n", [(0, 5), (1, 13)])

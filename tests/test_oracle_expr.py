@@ -64,6 +64,28 @@ def test_complete_add_gate_over_d4_matches_the_closed_form(orc, fid_name):
         assert got[i] == gp.complete_add_closed_form(P, si, wi, ai, i, 2), i
 
 
+class _Lit:
+    """integers -> Montgomery limbs of one field, for the gates that use rational literals"""
+    def __init__(self, orc, fid, P):
+        self.orc, self.fid, self.modulus = orc, fid, P
+    def __call__(self, v):
+        return self.orc.to_mont(self.fid, self.orc.ints_to_limbs([v % self.modulus]))[0]
+
+
+@pytest.mark.parametrize("fid_name", ["FP", "FQ"])
+def test_endomul_scalar_gate_matches_the_closed_form(orc, fid_name):
+    fid = getattr(orc, fid_name)
+    n, m, P, rnd, w, co, ints = _setup(orc, fid, 3, 33)
+    sel8, alphas = rnd(m, 970), rnd(11, 971)
+    rec = gp.endomul_scalar_gate(gp.Recorder(), alphas, _Lit(orc, fid, P))
+    assert rec.n_cached == 8 and rec.ops.count(8) == 8           # eight c_func values, each reused once (in b8_expected)
+    cols = [(a, 8) for a in w] + [(a, 8) for a in co] + [(sel8, 8)]
+    got = ints(orc.expr_eval(fid, rec.ops, rec.args, rec.literals, cols, m))
+    wi, si, ai = [ints(a) for a in w], ints(sel8), ints(alphas)
+    for i in list(range(0, m, 3)) + [m - 1]:
+        assert got[i] == gp.endomul_scalar_closed_form(P, si, wi, ai, i), i
+
+
 def test_failure_modes_of_the_reference(orc):
     one = orc.to_mont(orc.FP, orc.ints_to_limbs([1]))
     col = [(orc.to_mont(orc.FP, orc.random_scalars(orc.FP, 8, seed=3)), 8)]
