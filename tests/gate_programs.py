@@ -5,6 +5,8 @@
                                                                           MDS constants, next-row cells; evaluated over d8
   complete add     kimchi/src/circuits/polynomials/complete_add.rs:103-222   7 constraints, three cached sub-expressions (x21, y21,
                                                                           x1^2), the literal 1, doublings; degree 3, over d4
+  endomul          kimchi/src/circuits/polynomials/endosclmul.rs:475-549      12 constraints: the EndoCoefficient constant, squares (Pow 2),
+                                                                          eight cached sub-expressions, three next-row cells; degree 4+
   endomul scalar   kimchi/src/circuits/polynomials/endomul_scalar.rs:174-220  11 constraints: Horner polynomials with the rational
                                                                           literals 11/6, -5/2, 2/3, eight cached c_func values, long
                                                                           double-and-add folds; degree 4
@@ -236,3 +238,80 @@ def endomul_scalar_closed_form(P, sel, w, alpha_pows, i):
         b = (2 * b + poly(c_coeffs, x) + poly(d_minus_c, x)) % P
     cons = [n - n8, a - a8, b - b8] + [poly(crumb_over_x, x) * x for x in xs]
     return sel[i] * sum(al * c for al, c in zip(alpha_pows, cons)) % P
+
+
+
+def endomul_gate(p, alpha_pows, one, endo):
+    """selector * sum_k alpha^(e_k) * constraint_k, the 12 constraints of endosclmul.rs:479-548; `one`, `endo` Montgomery limbs of 1 and
+    of the endo coefficient (Constant(EndoCoefficient), resolved by the caller like every constant)"""
+    xt, yt, inv, xp, yp, n, xr, yr, s1, s3, b1, b2, b3, b4 = W + 0, W + 1, W + 2, W + 4, W + 5, W + 6, W + 7, W + 8, W + 9, W + 10, W + 11, W + 12, W + 13, W + 14
+    xs = lambda: p.cell(W + 4, True)            # env.witness_next(4)
+    ys = lambda: p.cell(W + 5, True)
+    slots = {}
+
+    def cached(name, build):
+        if name in slots:
+            p.load(slots[name])
+        else:
+            build()
+            slots[name] = p.store()
+
+    dbl = lambda: p.dup().add()
+    endo_minus_1 = lambda: p.literal(endo).literal(one).sub()
+    xq = lambda name, b: cached(name, lambda: (p.literal(one).cell(b), endo_minus_1(), p.mul().add().cell(xt).mul()))     # (1 + b (endo - 1)) xt
+    xq1, xq2 = (lambda: xq("xq1", b1)), (lambda: xq("xq2", b3))
+    yq = lambda b: (p.cell(b), dbl(), p.literal(one).sub().cell(yt).mul())                                                # (2 b - 1) yt
+    s1sq = lambda: cached("s1sq", lambda: p.cell(s1).pow(2))
+    s3sq = lambda: cached("s3sq", lambda: p.cell(s3).pow(2))
+    xp_xr = lambda: cached("xp_xr", lambda: p.cell(xp).cell(xr).sub())
+    xr_xs = lambda: cached("xr_xs", lambda: (p.cell(xr), xs(), p.sub()))
+    ys_yr = lambda: cached("ys_yr", lambda: (ys(), p.cell(yr).add()))
+    yr_yp = lambda: cached("yr_yp", lambda: p.cell(yr).cell(yp).add())
+    boolean = lambda b: (p.cell(b).pow(2).cell(b).sub())
+
+    def n_constraint():
+        p.cell(n); dbl(); p.cell(b1).add(); dbl(); p.cell(b2).add(); dbl(); p.cell(b3).add(); dbl(); p.cell(b4).add()
+        p.cell(W + 6, True).sub()
+
+    # the cache order of the reference: xq1, xq2, s1^2, s3^2, xp-xr, xr-xs, ys+yr, yr+yp are built BEFORE the constraint list
+    # (endosclmul.rs:502-523); here each is built where it is first used — the value of every constraint is the same
+    cons = [
+        lambda: boolean(b1), lambda: boolean(b2), lambda: boolean(b3), lambda: boolean(b4),
+        lambda: (xq1(), p.cell(xp).sub().cell(s1).mul(), yq(b2), p.cell(yp).sub(), p.sub()),
+        lambda: (p.cell(xp), dbl(), s1sq(), p.sub(), xq1(), p.add(), xp_xr(), p.cell(s1).mul(), yr_yp(), p.add(), p.mul(),
+                 p.cell(yp), dbl(), xp_xr(), p.mul(), p.sub()),
+        lambda: (yr_yp(), p.pow(2), xp_xr(), p.pow(2), s1sq(), xq1(), p.sub().cell(xr).add().mul(), p.sub()),
+        lambda: (xq2(), p.cell(xr).sub().cell(s3).mul(), yq(b4), p.cell(yr).sub(), p.sub()),
+        lambda: (p.cell(xr), dbl(), s3sq(), p.sub(), xq2(), p.add(), xr_xs(), p.cell(s3).mul(), ys_yr(), p.add(), p.mul(),
+                 p.cell(yr), dbl(), xr_xs(), p.mul(), p.sub()),
+        lambda: (ys_yr(), p.pow(2), xr_xs(), p.pow(2), s3sq(), xq2(), p.sub(), xs(), p.add().mul(), p.sub()),
+        n_constraint,
+        lambda: (xp_xr(), xr_xs(), p.mul().cell(inv).mul().literal(one).sub()),
+    ]
+    p.cell(SELECTOR)
+    for k, build in enumerate(cons):
+        p.literal(alpha_pows[k])
+        build()
+        p.mul()
+        if k:
+            p.add()
+    p.mul()
+    return p
+
+
+def endomul_closed_form(P, sel, w, alpha_pows, endo, i, m, next_shift):
+    j = (i + next_shift) % m
+    xt, yt, inv, xp, yp, n, xr, yr, s1, s3, b1, b2, b3, b4 = (w[k][i] for k in (0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14))
+    xs, ys, n_next = w[4][j], w[5][j], w[6][j]
+    xq1, xq2 = (1 + b1 * (endo - 1)) * xt, (1 + b3 * (endo - 1)) * xt
+    yq1, yq2 = (2 * b2 - 1) * yt, (2 * b4 - 1) * yt
+    cons = [b1 * b1 - b1, b2 * b2 - b2, b3 * b3 - b3, b4 * b4 - b4,
+            (xq1 - xp) * s1 - (yq1 - yp),
+            (2 * xp - s1 * s1 + xq1) * ((xp - xr) * s1 + yr + yp) - 2 * yp * (xp - xr),
+            (yr + yp) ** 2 - (xp - xr) ** 2 * (s1 * s1 - xq1 + xr),
+            (xq2 - xr) * s3 - (yq2 - yr),
+            (2 * xr - s3 * s3 + xq2) * ((xr - xs) * s3 + ys + yr) - 2 * yr * (xr - xs),
+            (ys + yr) ** 2 - (xr - xs) ** 2 * (s3 * s3 - xq2 + xs),
+            16 * n + 8 * b1 + 4 * b2 + 2 * b3 + b4 - n_next,
+            (xp - xr) * (xr - xs) * inv - 1]
+    return sel[i] * sum(a * c for a, c in zip(alpha_pows, cons)) % P

@@ -1,9 +1,9 @@
 """SURVEY.md §8f row 3, the evaluator: kimchi's expression framework on the device.  zk_expr_eval_dev runs the reference's RPN form
 of a constraint (PolishToken, kimchi/src/circuits/expr.rs:819-836) at every point of d4 / d8 with the semantics of
 PolishToken::evaluate (:856-940) and the cell indexing of Expr::evaluations (:1938-1990).  Checked bit for bit against the oracle's
-own restatement (pinned to the gates' closed forms in tests/test_oracle_expr.py) on the programs of four real gates
+own restatement (pinned to the gates' closed forms in tests/test_oracle_expr.py) on the programs of five real gates
 (generic: kimchi/src/circuits/polynomials/generic.rs:83-120; poseidon: poseidon.rs:351-436; complete add: complete_add.rs:103-222;
-endomul scalar: endomul_scalar.rs:174-220), on random programs that use every
+endomul: endosclmul.rs:475-549; endomul scalar: endomul_scalar.rs:174-220), on random programs that use every
 opcode, on the permutation quotient written as a program (against the dedicated kernel), and on the reference's failure modes."""
 import numpy as np
 import pytest
@@ -87,6 +87,22 @@ def test_endomul_scalar_gate_over_d8(ctx, orc, fid, log_n):
         cols = [(r.put(a), m, 8) for a in w + co] + [(r.put(sel8), m, 8)]
         d_out = r.alloc(m * 32)
         gp.endomul_scalar_gate(zk.ExprProgram(), alphas, _Lit(orc, fid)).evaluations(ctx, fid, cols, m, 8, d_out)
+        assert np.array_equal(ctx.dev_download(d_out, (m, 4)), want)
+
+
+@pytest.mark.parametrize("fid,log_n", [(1, 5), (0, 11)])
+def test_endomul_gate_over_d8(ctx, orc, fid, log_n):
+    """endosclmul.rs:475-549: 12 constraints with the endo coefficient as a literal, squares (Pow 2), eight cached sub-expressions and
+    three next-row cells (the last 8 rows of d8 wrap to row 0)"""
+    n, m, rnd, w, co = _columns(orc, fid, log_n, 44)
+    sel8, alphas, endo = rnd(m, 980), rnd(12, 981), rnd(1, 982)[0]
+    one = orc.to_mont(fid, orc.ints_to_limbs([1]))[0]
+    rec = gp.endomul_gate(gp.Recorder(), alphas, one, endo)
+    want = orc.expr_eval(fid, rec.ops, rec.args, rec.literals, [(a, 8) for a in w + co] + [(sel8, 8)], m)
+    with Resident(ctx) as r:
+        cols = [(r.put(a), m, 8) for a in w + co] + [(r.put(sel8), m, 8)]
+        d_out = r.alloc(m * 32)
+        gp.endomul_gate(zk.ExprProgram(), alphas, one, endo).evaluations(ctx, fid, cols, m, 8, d_out)
         assert np.array_equal(ctx.dev_download(d_out, (m, 4)), want)
 
 

@@ -86,6 +86,21 @@ def test_endomul_scalar_gate_matches_the_closed_form(orc, fid_name):
         assert got[i] == gp.endomul_scalar_closed_form(P, si, wi, ai, i), i
 
 
+@pytest.mark.parametrize("fid_name", ["FP", "FQ"])
+def test_endomul_gate_matches_the_closed_form(orc, fid_name):
+    fid = getattr(orc, fid_name)
+    n, m, P, rnd, w, co, ints = _setup(orc, fid, 3, 44)
+    sel8, alphas, endo = rnd(m, 980), rnd(12, 981), rnd(1, 982)[0]
+    one = orc.to_mont(fid, orc.ints_to_limbs([1]))[0]
+    rec = gp.endomul_gate(gp.Recorder(), alphas, one, endo)
+    assert rec.n_cached == 8
+    cols = [(a, 8) for a in w] + [(a, 8) for a in co] + [(sel8, 8)]
+    got = ints(orc.expr_eval(fid, rec.ops, rec.args, rec.literals, cols, m))
+    wi, si, ai, ei = [ints(a) for a in w], ints(sel8), ints(alphas), ints(endo[None])[0]
+    for i in list(range(0, m, 3)) + [m - 8, m - 1]:
+        assert got[i] == gp.endomul_closed_form(P, si, wi, ai, ei, i, m, 8), i
+
+
 def test_failure_modes_of_the_reference(orc):
     one = orc.to_mont(orc.FP, orc.ints_to_limbs([1]))
     col = [(orc.to_mont(orc.FP, orc.random_scalars(orc.FP, 8, seed=3)), 8)]
